@@ -1,0 +1,46 @@
+"""In-tree build of the CUDA library:  python -m acropolis_b200.build [--force]
+
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ...  -> acropolis_b200/libacropolis_b200.so
+(cross-compiles without a GPU; the .so travels to the GPU box with the repo snapshot)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", f) for f in ("acro_kernels.cu", "acro_api.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("acro_internal.h", "acro_physics.cuh")] + \
+    [os.path.join(HERE, "..", "include", "acropolis_b200.h")]
+OUT = os.path.join(HERE, "libacropolis_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def nvcc_path():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def up_to_date():
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(d) <= t for d in DEPS)
+
+
+def build_library(force=False, verbose=False):
+    if not force and up_to_date():
+        return OUT
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,967 @@
+// acro_kernels.cu -- hand-written sm_100a kernels of the ACROPOLIS hot path (FP64 throughout).
+//
+//   rates_kernel        thread per (system, E_i)        G[3,NE]: closed forms + rates.db bilinear interpolation
+//   direct_rates_kernel warp per out-of-table (E,T)     the two 2-D rate integrals the reference does with dblquad
+//   kernels_kernel      thread per (system, E_i, E_j>=i) five K planes: closed forms + three Planck-weighted
+//                                                       fixed-order Gauss-Legendre integrals in log(eps_bar)
+//   solve_pdi_kernel    warp per system                 back-substitution of the 3-species cascade equation,
+//                                                       fused with the 17 sigma(E)*F(E) rate integrals
+//   matrix_kernel       warp per point                  exact piecewise T-integral, 9x9 expm, decay matrices, Yf
+//   transfer_kernel     thread per matrix               fast-parameter path: expm(f*mpdi+mdcy) and Yf only
+//
+// None of this is a dense contraction, so no tensor-core (tcgen05) path exists for it: the bound is the FP64 pipe
+// for the quadrature kernels and HBM for solve/matrix.
+#include <cstdio>
+#include <vector>
+#include <cmath>
+
+#include "acro_internal.h"
+#include "acro_physics.cuh"
+
+namespace acro {
+
+// ------------------------------------------------------------------------------------------------------------
+// Gauss-Legendre tables in constant memory: orders 8, 16, 32, 64, 96, 128 packed back to back.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kGLTotal = 8 + 16 + 32 + 64 + 96 + 128;
+__constant__ double c_glx[kGLTotal];
+__constant__ double c_glw[kGLTotal];
+
+__host__ __device__ constexpr int gl_offset(int order) {
+    return order == 8 ? 0 : order == 16 ? 8 : order == 32 ? 24 : order == 64 ? 56 : order == 96 ? 120 : 216;
+}
+
+static void gauss_legendre(int n, double* x, double* w) {
+    // Newton iteration on P_n (long double), roots symmetric
+    for (int i = 0; i < (n + 1) / 2; ++i) {
+        long double z = cosl(3.14159265358979323846264338327950288L * (i + 0.75L) / (n + 0.5L)), pp = 0, z1;
+        do {
+            long double p1 = 1, p2 = 0;
+            for (int j = 0; j < n; ++j) {
+                long double p3 = p2;
+                p2 = p1;
+                p1 = ((2 * j + 1) * z * p2 - j * p3) / (j + 1);
+            }
+            pp = n * (z * p1 - p2) / (z * z - 1);
+            z1 = z;
+            z  = z1 - p1 / pp;
+        } while (fabsl(z - z1) > 1e-19L);
+        x[i]         = (double)(-z);
+        x[n - 1 - i] = (double)z;
+        w[i] = w[n - 1 - i] = (double)(2 / ((1 - z * z) * pp * pp));
+    }
+}
+
+cudaError_t upload_quadrature_tables() {
+    std::vector<double> x(kGLTotal), w(kGLTotal);
+    const int orders[6] = {8, 16, 32, 64, 96, 128};
+    for (int o : orders) gauss_legendre(o, x.data() + gl_offset(o), w.data() + gl_offset(o));
+    cudaError_t e = cudaMemcpyToSymbol(c_glx, x.data(), sizeof(double) * kGLTotal);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_glw, w.data(), sizeof(double) * kGLTotal);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ RateDb make_db(const DeviceTables& t) {
+    RateDb db;
+    db.tab = t.ratedb; db.nT = t.nT; db.nE = t.nE;
+    db.Elog_min = t.Elog_min; db.Elog_max = t.Elog_max; db.Tlog_min = t.Tlog_min; db.Tlog_max = t.Tlog_max;
+    return db;
+}
+
+// index of the system that owns flat entry `t` of a prefix array off[0..n) (off ascending, off[0]=0)
+__device__ __forceinline__ int owner_of(const int64_t* __restrict__ off, int n, int64_t t) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__host__ __device__ __forceinline__ int64_t tri_row_off(int i, int ne) {   // first entry of row i in packed upper-tri
+    return (int64_t)i * ne - ((int64_t)i * (i - 1)) / 2;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// (i.a)+(v)  total rates G[3,NE] per system
+//   photon:   photon-photon scattering + Compton + Bethe-Heitler + thermal pair creation (cascade.py:373-374)
+//   e-/e+:    inverse Compton                                                           (cascade.py:497-498)
+// ------------------------------------------------------------------------------------------------------------
+struct RateEval {
+    double g_ph, g_el;
+    int direct;   // bit0: photon pair creation must come from the direct integral, bit1: inverse Compton
+};
+
+__device__ inline RateEval eval_rates(double E, double T, const DeviceTables& t, const acro_params_t& p) {
+    const Densities d = densities(T, t.eta, t.Yp, t.YHe4);
+    RateEval r;
+    r.direct = 0;
+    r.g_ph = rate_photon_photon(E, T) + rate_compton(E, d.ne) + rate_bethe_heitler(E, d.nNZ2);
+    r.g_el = 0.0;
+    const double E_log = log10(E), T_log = log10(T);
+    const RateDb db = make_db(t);
+    const bool indb = p.use_db && in_rate_db(db, E_log, T_log);
+    if (!(E < kMe2 / (50.0 * T))) {   // pair-creation threshold (cascade.py:362)
+        if (indb) r.g_ph += interp_rate_db(db, 0, E_log, T_log);
+        else r.direct |= 1;
+    }
+    if (indb) r.g_el = interp_rate_db(db, 1, E_log, T_log);
+    else r.direct |= 2;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) rates_kernel(acro_batch_t b, double* __restrict__ G, DeviceTables t, acro_params_t p,
+                                                    DirectRateItem* __restrict__ items, int* __restrict__ item_count,
+                                                    int* __restrict__ status_sys) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= b.n_sys_energy_total) return;
+    const int s  = owner_of(b.sys_f_off, b.n_systems, tid);
+    const int i  = (int)(tid - b.sys_f_off[s]);
+    const int pt = b.sys_point[s];
+    const int ne = b.pt_ne[pt];
+    const double E = b.e_grid[b.pt_e_off[pt] + i];
+    const double T = b.sys_T[s];
+    const RateEval r = eval_rates(E, T, t, p);
+    double* g = G + b.sys_f_off[s] * 3;
+    g[i] = r.g_ph;
+    g[ne + i] = r.g_el;
+    g[2 * ne + i] = r.g_el;
+    if (r.direct) {
+        const int k = atomicAdd(item_count, 1);
+        DirectRateItem it;
+        it.g_index = b.sys_f_off[s] * 3 + i; it.ne = ne; it.kind = r.direct; it.E = E; it.T = T;
+        items[k] = it;
+        if (status_sys) status_sys[s] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// direct 2-D rate integrals (outside rates.db): one warp per item.
+//
+//  inverse Compton (cascade.py:469-485):  2 pi alpha^2/E^2 * int_0^ulim dx  x/(pi^2 (e^{x/T}-1)) int_x^{ymax(x)} dy F(y,E,x)
+//     outer: GL-64 in log x on [log(1e-9 T), log ulim] (the integrand ~ x^2 as x->0);
+//     inner: with w = 1 + Gamma q, y = E (1 - 1/w): GL-96 in s = log w on [log(1+Gamma q_min), log(1+Gamma)], dy = E/w ds.
+//  photon pair creation (cascade.py:336-358): 1/(8E^2) int dx 1/(pi^2 (e^{x/T}-1)) int_{4me^2}^{4Ex} ds s sigma_pc(s)
+//     outer: GL-128 in log x on [log(me^2/E), log(200 T)];
+//     inner: u = log(s/4me^2) = v^2 (removes the sqrt threshold of sigma_pc), GL-32 in v.
+//  Orders validated against the reference at eps=1e-9 (tools/proto/direct_rates_proto.py): <= 1e-7 relative.
+// ------------------------------------------------------------------------------------------------------------
+__device__ double direct_ic_lane(double E, double T, double Ephb_T_max, int lane) {
+    const double ulim = fmin(E - kMe2 / (4.0 * E), Ephb_T_max * T);
+    const double a = log(1e-9 * T), bq = log(ulim);
+    const double h = 0.5 * (bq - a), m = 0.5 * (bq + a);
+    const double* xo = c_glx + gl_offset(64); const double* wo = c_glw + gl_offset(64);
+    const double* xi = c_glx + gl_offset(96); const double* wi = c_glw + gl_offset(96);
+    double tot = 0.0;
+    for (int k = lane; k < 64; k += 32) {
+        const double x  = exp(m + h * xo[k]);
+        const double Gm = 4.0 * x * E / kMe2;
+        const double qmin = x / (Gm * (E - x));
+        const double s0 = log1p(Gm * qmin), s1 = log1p(Gm);
+        const double hs = 0.5 * (s1 - s0), ms = 0.5 * (s1 + s0);
+        double inner = 0.0;
+        for (int j = 0; j < 96; ++j) {
+            const double s  = ms + hs * xi[j];
+            const double w  = exp(s);
+            const double y  = E * expm1(s) / w;
+            const double q  = y / (Gm * (E - y));
+            const double Gq = Gm * q;
+            const double F  = 2.0 * q * log(q) + (1.0 + 2.0 * q) * (1.0 - q) + Gq * Gq * (1.0 - q) / (2.0 + 2.0 * Gq);
+            inner += wi[j] * F * E / w;
+        }
+        inner *= hs;
+        tot += h * wo[k] * inner * x / (kPi2 * expm1(x / T)) * x;
+    }
+    return 2.0 * kPi * (kAlpha * kAlpha) * tot / (E * E);
+}
+
+__device__ double direct_pc_lane(double E, double T, double Ephb_T_max, int lane) {
+    const double a = log(kMe2 / E), bq = log(Ephb_T_max * T);
+    const double h = 0.5 * (bq - a), m = 0.5 * (bq + a);
+    const double* xo = c_glx + gl_offset(128); const double* wo = c_glw + gl_offset(128);
+    const double* xi = c_glx + gl_offset(32);  const double* wi = c_glw + gl_offset(32);
+    double tot = 0.0;
+    for (int k = lane; k < 128; k += 32) {
+        const double x = exp(m + h * xo[k]);
+        const double vmax = sqrt(log(E * x / kMe2));
+        double inner = 0.0;
+        for (int j = 0; j < 32; ++j) {
+            const double v  = 0.5 * vmax * (1.0 + xi[j]);
+            const double u  = v * v;
+            const double s  = 4.0 * kMe2 * exp(u);
+            const double b2 = -expm1(-u), bb = sqrt(b2);
+            const double sig = 0.5 * kPi * (kRe * kRe) * (1.0 - b2) *
+                               ((3.0 - b2 * b2) * log((1.0 + bb) / (1.0 - bb)) - 2.0 * bb * (2.0 - b2));
+            inner += wi[j] * s * sig * s * 2.0 * v;
+        }
+        inner *= 0.5 * vmax;
+        tot += h * wo[k] * inner / (kPi2 * expm1(x / T)) * x;
+    }
+    return tot / (8.0 * E * E);
+}
+
+__global__ void __launch_bounds__(128) direct_rates_kernel(double* __restrict__ G, const DirectRateItem* __restrict__ items,
+                                                           const int* __restrict__ item_count, acro_params_t p) {
+    const int n = *item_count;
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps_total) {
+        const DirectRateItem it = items[w];
+        if (it.kind & 1) {
+            const double v = warp_sum(direct_pc_lane(it.E, it.T, p.Ephb_T_max, lane));
+            if (lane == 0) G[it.g_index] += v;
+        }
+        if (it.kind & 2) {
+            const double v = warp_sum(direct_ic_lane(it.E, it.T, p.Ephb_T_max, lane));
+            if (lane == 0) { G[it.g_index + it.ne] = v; G[it.g_index + 2 * (int64_t)it.ne] = v; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// (i.b)  kernel planes.  One thread per (system, i, j>=i).
+//   plane 0  gamma->gamma : photon-photon scattering + Compton                          (cascade.py:439-442)
+//   plane 1  e+-  ->gamma : inverse Compton, thermal integral                          (cascade.py:406-435)
+//   plane 2  gamma->e-    : Compton (recoil electron) + Bethe-Heitler + gamma gamma_th  (cascade.py:644-647)
+//   plane 3  gamma->e+    : Bethe-Heitler + gamma gamma_th                              (cascade.py:684-687)
+//   plane 4  e+-  ->e+-   : inverse Compton, thermal integral                          (cascade.py:507-540)
+// The thermal integrals run over log(eps_bar) with a Q-point Gauss-Legendre rule (Q = quad_order); the
+// reference uses adaptive QAGS at epsrel=1e-3, which GL-64 reproduces to <=1.4e-10.
+// ------------------------------------------------------------------------------------------------------------
+template <int Q>
+__device__ __forceinline__ double integral_ic_photon(double E, double Ep, double T, double llim, double ulim) {
+    const double a = log(llim), b = log(ulim);
+    const double h = 0.5 * (b - a), m = 0.5 * (b + a);
+    const double iT = 1.0 / T;
+    double sum = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < Q; ++k) {
+        const double x = exp(fma(h, c_glx[gl_offset(Q) + k], m));
+        const double f = ic_F(E, Ep, x) * (x * x) / (exp(x * iT) - 1.0);
+        sum = fma(c_glw[gl_offset(Q) + k], f, sum);
+    }
+    return sum * h * (1.0 / kPi2);
+}
+
+template <int Q>
+__device__ __forceinline__ double integral_ic_electron(double E, double Ep, double T, double llim, double ulim) {
+    const double a = log(llim), b = log(ulim);
+    const double h = 0.5 * (b - a), m = 0.5 * (b + a);
+    const double iT = 1.0 / T;
+    const double dE = Ep - E;
+    double sum = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < Q; ++k) {
+        const double x = exp(fma(h, c_glx[gl_offset(Q) + k], m));
+        const double f = ic_F(dE + x, Ep, x) * (x * x) / (exp(x * iT) - 1.0);
+        sum = fma(c_glw[gl_offset(Q) + k], f, sum);
+    }
+    return sum * h * (1.0 / kPi2);
+}
+
+template <int Q>
+__device__ __forceinline__ double integral_pc_electron(double E, double Ep, double T, double llim, double ulim) {
+    const double a = log(llim), b = log(ulim);
+    const double h = 0.5 * (b - a), m = 0.5 * (b + a);
+    const double iT = 1.0 / T;
+    double sum = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < Q; ++k) {
+        const double x = exp(fma(h, c_glx[gl_offset(Q) + k], m));
+        const double f = pc_G(E, Ep, x) * x / (exp(x * iT) - 1.0);
+        sum = fma(c_glw[gl_offset(Q) + k], f, sum);
+    }
+    return sum * h * (1.0 / kPi2);
+}
+
+struct KernelEntry { double gg, eg, gem, gep, ee; };
+
+template <int Q>
+__device__ __forceinline__ KernelEntry eval_kernels(double E, double Ep, double T, const Densities d, double Ephb_T_max) {
+    KernelEntry k;
+    const double xmax = Ephb_T_max * T;
+    // gamma -> gamma
+    k.gg = kernel_photon_photon(E, Ep, T) + kernel_compton_core(E, Ep, d.ne);
+    // e -> gamma (inverse Compton), cascade.py:406-435
+    k.eg = 0.0;
+    const bool above = !(Ep < E + kMe);
+    if (above) {
+        const double llim = 0.25 * kMe2 * E / (Ep * Ep - Ep * E);
+        const double ulim = fmin(fmin(E, Ep - kMe2 / (4.0 * Ep)), xmax);
+        if (ulim > llim) k.eg = 2.0 * kPi * (kAlpha * kAlpha) * integral_ic_photon<Q>(E, Ep, T, llim, ulim) / (Ep * Ep);
+    }
+    // e -> e (inverse Compton), cascade.py:507-540
+    k.ee = 0.0;
+    if (E != Ep) {
+        const double pf = 0.25 * kMe2 / Ep - E;
+        const double qf = 0.25 * kMe2 * (Ep - E) / Ep;
+        const double sq = sqrt((0.5 * pf) * (0.5 * pf) - qf);
+        const double z1 = -0.5 * pf - sq, z2 = -0.5 * pf + sq;
+        const double ulim = fmin(fmin(z2, Ep - kMe2 / (4.0 * Ep)), xmax);
+        if (ulim > z1) k.ee = 2.0 * kPi * (kAlpha * kAlpha) * integral_ic_electron<Q>(E, Ep, T, z1, ulim) / (Ep * Ep);
+    }
+    // gamma -> e-/e+ : Bethe-Heitler (cascade.py:550-558) + gamma gamma_th -> e+ e- (cascade.py:562-598)
+    double pair = 0.0;
+    if (above) pair = d.nNZ2 * bh_dsdE_Z2(E, Ep);
+    if (!(Ep < kMe2 / (50.0 * T))) {
+        const double dE = Ep - E, rt = sqrt(E * E - kMe2), den = 4.0 * Ep * dE + kMe2;
+        const double z1 = Ep * (kMe2 - 2.0 * dE * (rt - E)) / den;
+        const double z2 = Ep * (kMe2 + 2.0 * dE * (rt + E)) / den;
+        const double llim = fmax(kMe2 / Ep, z1);
+        const double ulim = fmin(fmin(z2, Ep), xmax);
+        if (ulim > llim)
+            pair += 0.25 * kPi * (kAlpha * kAlpha) * kMe2 * integral_pc_electron<Q>(E, Ep, T, llim, ulim) / (Ep * Ep * Ep);
+    }
+    k.gep = pair;
+    // Compton recoil electron: the photon formula with E -> Ep + me - E (cascade.py:621-639)
+    k.gem = pair + kernel_compton_core(Ep + kMe - E, Ep, d.ne);
+    return k;
+}
+
+template <int Q>
+__global__ void __launch_bounds__(128) kernels_kernel(acro_batch_t b, double* __restrict__ Kws, DeviceTables t, acro_params_t p) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= b.n_pairs_total) return;
+    const int s  = owner_of(b.sys_k_off, b.n_systems, tid);
+    const int64_t loc = tid - b.sys_k_off[s];
+    const int pt = b.sys_point[s];
+    const int ne = b.pt_ne[pt];
+    // invert loc = i*ne - i(i-1)/2 + (j-i)
+    const double tn = 2.0 * ne + 1.0;
+    int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+    if (i < 0) i = 0;
+    if (i > ne - 1) i = ne - 1;
+    while (i > 0 && tri_row_off(i, ne) > loc) --i;
+    while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
+    const int j = i + (int)(loc - tri_row_off(i, ne));
+    const double* eg = b.e_grid + b.pt_e_off[pt];
+    const double E = eg[i], Ep = eg[j], T = b.sys_T[s];
+    const Densities d = densities(T, t.eta, t.Yp, t.YHe4);
+    const KernelEntry k = eval_kernels<Q>(E, Ep, T, d, p.Ephb_T_max);
+    const int64_t np = b.n_pairs_total;
+    Kws[tid]          = k.gg;
+    Kws[np + tid]     = k.eg;
+    Kws[2 * np + tid] = k.gem;
+    Kws[3 * np + tid] = k.gep;
+    Kws[4 * np + tid] = k.ee;
+}
+
+// dense copy of one system's planes (debug / parity checks)
+__global__ void unpack_kernels_kernel(const double* __restrict__ Kws, int64_t np, int64_t k_off, int ne, double* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 5 * ne * ne) return;
+    const int k = idx / (ne * ne), r = idx % (ne * ne), i = r / ne, j = r % ne;
+    out[idx] = (j >= i) ? Kws[(int64_t)k * np + k_off + tri_row_off(i, ne) + (j - i)] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// (ii)+(iii)  cascade back-substitution fused with the photodisintegration-rate integrals.  One warp per system.
+//
+// Cascade equation on the log-energy grid, trapezoid weights (cascade.py:180-239): rows are solved from the top
+// energy down; the sum over j>i is split across the lanes and combined with warp shuffles; the 3x3 system per row
+// is solved with partial pivoting.  wF[X][j] holds weight_j * F_X(E_j) (for j = NE-1 the delta-source term
+// S0_X/Gamma_X(E0) is folded in), so one fused multiply-add per kernel entry remains.
+// Then Gamma_r = S0_gamma sigma_r(E0)/Gamma_gamma(E0) + int_{Eth}^{Emax} F_gamma(E) E sigma_r(E) dlogE with
+// F_gamma the log-log interpolant of the grid values (nucl.py:398-467, utils.py:38-61), integrated exactly cell
+// by cell (GL-8 per cell; the threshold cell with a quadratic substitution) instead of adaptive QAGS.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void solve3(double B[3][3], double a[3], double x[3]) {
+    // Gaussian elimination with partial pivoting (the reference calls LAPACK dgesv, cascade.py:221)
+    int p[3] = {0, 1, 2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int piv = c;
+        double best = fabs(B[p[c]][c]);
+#pragma unroll
+        for (int r = c + 1; r < 3; ++r) {
+            const double v = fabs(B[p[r]][c]);
+            if (v > best) { best = v; piv = r; }
+        }
+        const int tmp = p[c]; p[c] = p[piv]; p[piv] = tmp;
+#pragma unroll
+        for (int r = c + 1; r < 3; ++r) {
+            const double f = B[p[r]][c] / B[p[c]][c];
+#pragma unroll
+            for (int cc = c; cc < 3; ++cc) B[p[r]][cc] -= f * B[p[c]][cc];
+            a[p[r]] -= f * a[p[c]];
+        }
+    }
+#pragma unroll
+    for (int c = 2; c >= 0; --c) {
+        double v = a[p[c]];
+#pragma unroll
+        for (int cc = c + 1; cc < 3; ++cc) v -= B[p[c]][cc] * x[cc];
+        x[c] = v / B[p[c]][c];
+    }
+}
+
+__device__ __forceinline__ double sc_value(const acro_batch_t& b, int s, int pt, int ne, int X, int i) {
+    if (b.sc_mode == ACRO_SC_NONE) return 0.0;
+    if (b.sc_mode == ACRO_SC_SEPARABLE) return b.sc[(int64_t)s * 3 + X] * b.sc_E[(b.pt_e_off[pt] + i) * 3 + X];
+    return b.sc[b.sys_f_off[s] * 3 + (int64_t)X * ne + i];
+}
+
+__global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const double* __restrict__ G, double* __restrict__ Fout,
+                                                        double* __restrict__ pdi, const double* __restrict__ Kws,
+                                                        acro_params_t p, int smem_stride) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int s = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (s >= b.n_systems) return;
+    const int pt = b.sys_point[s];
+    const int ne = b.pt_ne[pt];
+    const double* E = b.e_grid + b.pt_e_off[pt];
+    const double T = b.sys_T[s];
+    const double* g = G + b.sys_f_off[s] * 3;
+    double* wF  = smem + (size_t)wib * smem_stride;   // [3][ne]
+    double* lnF = wF + 3 * (size_t)ne;                // [ne]  log of the floored photon spectrum
+    double* lnE = lnF + ne;                           // [ne]
+    const int64_t np = b.n_pairs_total;
+    const double* K0 = Kws + b.sys_k_off[s];
+    const double S0[3] = {b.s0[(int64_t)s * 3], b.s0[(int64_t)s * 3 + 1], b.s0[(int64_t)s * 3 + 2]};
+    const int top = ne - 1;
+    const double dy = log(E[top] / p.Emin) / (double)(ne - 1);
+    double* fo = Fout ? Fout + b.sys_f_off[s] * 3 : nullptr;
+
+    // --- top row (cascade.py:194-198)
+    {
+        const int64_t r = tri_row_off(top, ne);
+        const double kgg = K0[r], keg = K0[np + r], kgm = K0[2 * np + r], kgp = K0[3 * np + r], kee = K0[4 * np + r];
+        const double G0 = g[top], G1 = g[ne + top], G2 = g[2 * ne + top];
+        double F[3];
+        F[0] = sc_value(b, s, pt, ne, 0, top) / G0 + (kgg * S0[0] / (G0 * G0) + keg * S0[1] / (G1 * G0) + keg * S0[2] / (G2 * G0));
+        F[1] = sc_value(b, s, pt, ne, 1, top) / G1 + (kgm * S0[0] / (G0 * G1) + kee * S0[1] / (G1 * G1));
+        F[2] = sc_value(b, s, pt, ne, 2, top) / G2 + (kgp * S0[0] / (G0 * G2) + kee * S0[2] / (G2 * G2));
+        if (lane == 0) {
+            const double hw = 0.5 * dy * E[top];
+            wF[top]          = S0[0] / G0 + hw * F[0];
+            wF[ne + top]     = S0[1] / G1 + hw * F[1];
+            wF[2 * ne + top] = S0[2] / G2 + hw * F[2];
+            lnF[top] = log(fmax(F[0], p.approx_zero));
+            if (fo) {
+                fo[top] = fmax(F[0], p.approx_zero);
+                fo[ne + top] = fmax(F[1], p.approx_zero);
+                fo[2 * ne + top] = fmax(F[2], p.approx_zero);
+            }
+        }
+    }
+    for (int i = lane; i < ne; i += 32) lnE[i] = log(E[i]);
+    __syncwarp();
+
+    // --- rows NE-2 .. 0 (cascade.py:201-224)
+    for (int i = top - 1; i >= 0; --i) {
+        const int64_t r = tri_row_off(i, ne);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int j = i + 1 + lane; j < ne; j += 32) {
+            const int64_t e = r + (j - i);
+            const double f0 = wF[j], f1 = wF[ne + j], f2 = wF[2 * ne + j];
+            const double kee = K0[4 * np + e];
+            a0 = fma(K0[e], f0, fma(K0[np + e], f1 + f2, a0));
+            a1 = fma(K0[2 * np + e], f0, fma(kee, f1, a1));
+            a2 = fma(K0[3 * np + e], f0, fma(kee, f2, a2));
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        const double Ei = E[i], hw = 0.5 * dy * Ei;
+        const double kgg = K0[r], keg = K0[np + r], kgm = K0[2 * np + r], kgp = K0[3 * np + r], kee = K0[4 * np + r];
+        double B[3][3] = {{g[i] - hw * kgg, -hw * keg, -hw * keg},
+                          {-hw * kgm, g[ne + i] - hw * kee, 0.0},
+                          {-hw * kgp, 0.0, g[2 * ne + i] - hw * kee}};
+        double a[3] = {a0 + sc_value(b, s, pt, ne, 0, i), a1 + sc_value(b, s, pt, ne, 1, i), a2 + sc_value(b, s, pt, ne, 2, i)};
+        double F[3];
+        solve3(B, a, F);
+        if (lane == 0) {
+            const double w = dy * Ei;
+            wF[i] = w * F[0]; wF[ne + i] = w * F[1]; wF[2 * ne + i] = w * F[2];
+            lnF[i] = log(fmax(F[0], p.approx_zero));
+            if (fo) {
+                fo[i] = fmax(F[0], p.approx_zero);
+                fo[ne + i] = fmax(F[1], p.approx_zero);
+                fo[2 * ne + i] = fmax(F[2], p.approx_zero);
+            }
+        }
+        __syncwarp();
+    }
+    if (!pdi) return;
+
+    // --- photodisintegration rates (nucl.py:398-467)
+    const double E0 = b.pt_e0[pt];
+    const double EC = kMe2 / (22.0 * T);
+    const double Emax = fmin(E0, p.E_EC_max * EC);
+    const double lnEmax = log(Emax);
+    const int nq = p.pdi_cell_order;   // 8 or 16
+    const double* qx = c_glx + gl_offset(nq);
+    const double* qw = c_glw + gl_offset(nq);
+    double acc[ACRO_NR];
+#pragma unroll
+    for (int r = 0; r < ACRO_NR; ++r) acc[r] = 0.0;
+    // (A) cells that lie entirely above a reaction's threshold: nodes shared by all reactions
+    for (int c = lane; c < ne - 1; c += 32) {
+        const double y0 = lnE[c], y1 = lnE[c + 1];
+        const double hi = fmin(y1, lnEmax);
+        if (!(hi > y0)) continue;
+        const double ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
+        const double bs = lnF[c + 1] - ms * y1;
+        const double h = 0.5 * (hi - y0), m = 0.5 * (hi + y0);
+        const double Elo = E[c];
+        for (int k = 0; k < nq; ++k) {
+            const double y  = fma(h, qx[k], m);
+            const double Ev = exp(y);
+            const double fe = qw[k] * h * exp(fma(ms, y, bs)) * Ev;
+#pragma unroll
+            for (int r = 0; r < ACRO_NR; ++r)
+                if (kEth[r] <= Elo) acc[r] = fma(fe, cross_section_mb(r + 1, Ev, y), acc[r]);
+        }
+    }
+    // (B) the threshold cell of each reaction: lane r integrates [log Eth_r, min(cell end, log Emax)] with
+    //     y = lo + (hi-lo) u^2, which regularises the (E-Q)^p onset of the cross-sections.
+    double thr = 0.0;
+    if (lane < ACRO_NR) {
+        const double Eth = kEth[lane];
+        if (Emax > Eth && Eth > E[0]) {
+            const double lo = log(Eth);
+            // c = last grid index with E[c] < Eth (cells with E[c] >= Eth are covered by part A)
+            int c = (int)((lo - lnE[0]) * (double)(ne - 1) / (lnE[ne - 1] - lnE[0]));
+            c = max(0, min(c, ne - 2));
+            while (c > 0 && !(E[c] < Eth)) --c;
+            while (c < ne - 2 && E[c + 1] < Eth) ++c;
+            const double y0 = lnE[c], y1 = lnE[c + 1];
+            const double hi = fmin(y1, lnEmax);
+            if (hi > lo) {
+                const double ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
+                const double bs = lnF[c + 1] - ms * y1;
+                const double* tx = c_glx + gl_offset(16);
+                const double* tw = c_glw + gl_offset(16);
+                for (int k = 0; k < 16; ++k) {
+                    const double u  = 0.5 * (1.0 + tx[k]);
+                    const double y  = fma(hi - lo, u * u, lo);
+                    const double Ev = exp(y);
+                    thr = fma(tw[k] * 0.5 * (hi - lo) * 2.0 * u * exp(fma(ms, y, bs)) * Ev, cross_section_mb(lane + 1, Ev, y), thr);
+                }
+            }
+        }
+    }
+    const double rate_E0 = g[top];   // Gamma_gamma(E0, T): the grid's last point is E0 (cascade.py:745, nucl.py:436)
+#pragma unroll
+    for (int r = 0; r < ACRO_NR; ++r) {
+        double v = warp_sum(acc[r]);
+        v += __shfl_sync(0xffffffffu, thr, r);
+        if (lane == 0) {
+            double rate = S0[0] * cross_section(r + 1, E0) / rate_E0;
+            if (Emax > kEth[r]) rate += kMbToIMeV2 * v;
+            pdi[(int64_t)s * ACRO_NR + r] = fmax(p.approx_zero, rate);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// (iv)  T-integral of the rate matrix, 9x9 matrix exponential, pre/post decay matrices, final abundances.
+// ------------------------------------------------------------------------------------------------------------
+// stoichiometry of the 17 reactions and the 2 decays (nucl.py:49-67,116-120,144-171): initial nuclide and final
+// multiplicities over (n,p,d,t,He3,He4,Li6,Li7,Be7)
+__constant__ const signed char kReacInit[ACRO_NR] = {2, 3, 3, 4, 4, 5, 5, 5, 5, 6, 6, 7, 7, 7, 8, 8, 8};
+__constant__ const signed char kReacFinal[ACRO_NR][ACRO_NY] = {
+    {1, 1, 0, 0, 0, 0, 0, 0, 0},   //  1 d+a>n+p
+    {1, 0, 1, 0, 0, 0, 0, 0, 0},   //  2 t+a>n+d
+    {2, 1, 0, 0, 0, 0, 0, 0, 0},   //  3 t+a>n+p+n
+    {0, 1, 1, 0, 0, 0, 0, 0, 0},   //  4 He3+a>p+d
+    {1, 2, 0, 0, 0, 0, 0, 0, 0},   //  5 He3+a>n+p+p
+    {0, 1, 0, 1, 0, 0, 0, 0, 0},   //  6 He4+a>p+t
+    {1, 0, 0, 0, 1, 0, 0, 0, 0},   //  7 He4+a>n+He3
+    {0, 0, 2, 0, 0, 0, 0, 0, 0},   //  8 He4+a>d+d
+    {1, 1, 1, 0, 0, 0, 0, 0, 0},   //  9 He4+a>n+p+d
+    {1, 1, 0, 0, 0, 1, 0, 0, 0},   // 10 Li6+a>n+p+He4
+    {0, 0, 0, 0, 0, 0, 0, 0, 0},   // 11 Li6+a>X
+    {0, 0, 0, 1, 0, 1, 0, 0, 0},   // 12 Li7+a>t+He4
+    {1, 0, 0, 0, 0, 0, 1, 0, 0},   // 13 Li7+a>n+Li6
+    {2, 1, 0, 0, 0, 1, 0, 0, 0},   // 14 Li7+a>n+n+p+He4
+    {0, 0, 0, 0, 1, 1, 0, 0, 0},   // 15 Be7+a>He3+He4
+    {0, 1, 0, 0, 0, 0, 1, 0, 0},   // 16 Be7+a>p+Li6
+    {1, 2, 0, 0, 0, 1, 0, 0, 0}};  // 17 Be7+a>p+p+n+He4
+
+// ---- 9x9 helpers (row-major, thread-local) ----
+__device__ inline void mm9(const double* A, const double* B, double* C) {
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 9; ++k) s = fma(A[i * 9 + k], B[k * 9 + j], s);
+            C[i * 9 + j] = s;
+        }
+}
+
+// Pade-13 scaling and squaring (Higham 2005, the algorithm behind scipy.linalg.expm used at models.py:130)
+__device__ void expm9(const double* Ain, double* R) {
+    const double b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
+                          10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
+    double A[81], A2[81], A4[81], A6[81], U[81], V[81], W[81];
+    double nrm = 0.0;
+    for (int j = 0; j < 9; ++j) {
+        double c = 0.0;
+        for (int i = 0; i < 9; ++i) c += fabs(Ain[i * 9 + j]);
+        nrm = fmax(nrm, c);
+    }
+    int s = 0;
+    if (nrm > 5.371920351148152) s = (int)fmax(0.0, ceil(log2(nrm / 5.371920351148152)));
+    const double sc = ldexp(1.0, -s);
+    for (int i = 0; i < 81; ++i) A[i] = Ain[i] * sc;
+    mm9(A, A, A2); mm9(A2, A2, A4); mm9(A4, A2, A6);
+    for (int i = 0; i < 81; ++i) W[i] = b[13] * A6[i] + b[11] * A4[i] + b[9] * A2[i];
+    mm9(A6, W, V);   // V = A6*W (temp)
+    for (int i = 0; i < 81; ++i) W[i] = V[i] + b[7] * A6[i] + b[5] * A4[i] + b[3] * A2[i] + ((i % 10 == 0) ? b[1] : 0.0);
+    mm9(A, W, U);
+    for (int i = 0; i < 81; ++i) W[i] = b[12] * A6[i] + b[10] * A4[i] + b[8] * A2[i];
+    mm9(A6, W, V);
+    for (int i = 0; i < 81; ++i) V[i] += b[6] * A6[i] + b[4] * A4[i] + b[2] * A2[i] + ((i % 10 == 0) ? b[0] : 0.0);
+    // solve (V-U) R = (V+U) by LU with partial pivoting
+    for (int i = 0; i < 81; ++i) { W[i] = V[i] - U[i]; R[i] = V[i] + U[i]; }
+    for (int c = 0; c < 9; ++c) {
+        int piv = c;
+        double best = fabs(W[c * 9 + c]);
+        for (int r = c + 1; r < 9; ++r) { const double v = fabs(W[r * 9 + c]); if (v > best) { best = v; piv = r; } }
+        if (piv != c)
+            for (int k = 0; k < 9; ++k) {
+                double t = W[c * 9 + k]; W[c * 9 + k] = W[piv * 9 + k]; W[piv * 9 + k] = t;
+                t = R[c * 9 + k]; R[c * 9 + k] = R[piv * 9 + k]; R[piv * 9 + k] = t;
+            }
+        const double ip = 1.0 / W[c * 9 + c];
+        for (int r = c + 1; r < 9; ++r) {
+            const double f = W[r * 9 + c] * ip;
+            if (f == 0.0) continue;
+            for (int k = c; k < 9; ++k) W[r * 9 + k] -= f * W[c * 9 + k];
+            for (int k = 0; k < 9; ++k) R[r * 9 + k] -= f * R[c * 9 + k];
+        }
+    }
+    for (int c = 8; c >= 0; --c) {
+        const double ip = 1.0 / W[c * 9 + c];
+        for (int k = 0; k < 9; ++k) {
+            double v = R[c * 9 + k];
+            for (int cc = c + 1; cc < 9; ++cc) v -= W[c * 9 + cc] * R[cc * 9 + k];
+            R[c * 9 + k] = v * ip;
+        }
+    }
+    for (int q = 0; q < s; ++q) {
+        mm9(R, R, W);
+        for (int i = 0; i < 81; ++i) R[i] = W[i];
+    }
+}
+
+// Yf = postd . expm(A) . pred . Y0 for the three abundance columns (models.py:77-89,133-157)
+__device__ void apply_transfer(const double* A, double t_at_tmax, const double* Y0 /*[9][3]*/, double* expm_out,
+                               double* Yf /*[9][3]*/, int* nonfinite) {
+    double R[81];
+    expm9(A, R);
+    if (expm_out) for (int i = 0; i < 81; ++i) expm_out[i] = R[i];
+    const double ef = exp(-t_at_tmax / kTauT);
+    bool bad = false;
+    for (int c = 0; c < 3; ++c) {
+        double y[9], z[9];
+        for (int i = 0; i < 9; ++i) y[i] = Y0[i * 3 + c];
+        // pre-decay: n -> p completely, t -> He3 by exp(-t(Tmax)/tau_t)
+        y[1] += y[0]; y[0] = 0.0;
+        y[4] += (1.0 - ef) * y[3]; y[3] = ef * y[3];
+        for (int i = 0; i < 9; ++i) {
+            double v = 0.0;
+            for (int k = 0; k < 9; ++k) v = fma(R[i * 9 + k], y[k], v);
+            z[i] = v;
+        }
+        // post-decay: n -> p, t -> He3, Be7 -> Li7
+        z[1] += z[0]; z[0] = 0.0;
+        z[4] += z[3]; z[3] = 0.0;
+        z[7] += z[8]; z[8] = 0.0;
+        for (int i = 0; i < 9; ++i) { Yf[i * 3 + c] = z[i]; bad |= !isfinite(z[i]); }
+    }
+    if (bad) *nonfinite = 1;
+}
+
+// int_{x1}^{x2} 10^{alpha x + beta} ln10 dx, stable for any alpha (evaluated from the larger end)
+__device__ __forceinline__ double pow10_segment(double alpha, double beta, double x1, double x2) {
+    const double ln10 = 2.302585092994046;
+    const double dx = x2 - x1;
+    const double z = alpha * ln10 * dx;
+    if (z >= 0.0) {
+        const double top = exp((alpha * x2 + beta) * ln10);
+        const double phi = (z > 1e-8) ? -expm1(-z) / z : 1.0 - 0.5 * z;
+        return ln10 * top * dx * phi;
+    }
+    const double bot = exp((alpha * x1 + beta) * ln10);
+    const double phi = (z < -1e-8) ? expm1(z) / z : 1.0 + 0.5 * z;
+    return ln10 * bot * dx * phi;
+}
+
+// One warp per point.  Integrates Gamma_r(T) T / |dT/dt| dlogT exactly: both factors are piecewise power laws
+// (log10-log10 linear on the NT-point rate grid, utils.py:38-61, and on the cosmo table, input.py:205-226), so
+// each sub-cell has the closed form of pow10_segment; no quadrature (the reference uses QAGS, nucl.py:613-614).
+__global__ void __launch_bounds__(32) matrix_kernel(int n_points, const int32_t* __restrict__ pt_nt,
+                                                    const int32_t* __restrict__ pt_sys_off, const double* __restrict__ sys_T,
+                                                    const double* __restrict__ pdi, const double* __restrict__ T_lo,
+                                                    const double* __restrict__ pt_t_at_tmax, const int* __restrict__ status_sys,
+                                                    const double* __restrict__ pt_e0, double* __restrict__ mpdi_out,
+                                                    double* __restrict__ mdcy_out, double* __restrict__ Yf_out,
+                                                    int32_t* __restrict__ status_out, DeviceTables t, acro_params_t p) {
+    extern __shared__ double sm[];
+    const int pt = blockIdx.x, lane = threadIdx.x;
+    if (pt >= n_points) return;
+    const int nt = pt_nt[pt], s0 = pt_sys_off[pt];
+    double* X = sm;             // [nt] log10 T
+    double* Y = sm + nt;        // [17][nt] log10 rate
+    for (int k = lane; k < nt; k += 32) {
+        X[k] = log10(sys_T[s0 + k]);
+        for (int r = 0; r < ACRO_NR; ++r) Y[r * nt + k] = log10(pdi[(int64_t)(s0 + k) * ACRO_NR + r]);
+    }
+    __syncwarp();
+    int st = 0;
+    if (status_sys)
+        for (int k = lane; k < nt; k += 32) st |= status_sys[s0 + k] ? ACRO_ST_DIRECT_RATE : 0;
+    const double x_hi = X[nt - 1];
+    double x_lo = X[0];
+    if (T_lo) x_lo = fmin(fmax(log10(T_lo[pt]), X[0]), x_hi);
+    const double* LT = t.cosmo_lT;      // descending
+    const double* LD = t.cosmo_ldTdt;
+    const int nc = t.n_cosmo;
+    if (!(LT[nc - 1] <= x_lo && x_hi <= LT[0])) st |= ACRO_ST_T_OUTSIDE;
+    // cosmo cell c spans [LT[c+1], LT[c]]; first cell containing x_hi and last cell containing x_lo
+    int lo = 0, hi = nc - 2;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (LT[mid + 1] < x_hi) hi = mid; else lo = mid + 1; }
+    const int c_first = lo;
+    lo = 0; hi = nc - 2;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (LT[mid + 1] <= x_lo) hi = mid; else lo = mid + 1; }
+    const int c_last = lo;
+    double acc[ACRO_NR + 1];
+#pragma unroll
+    for (int r = 0; r <= ACRO_NR; ++r) acc[r] = 0.0;
+    const double inv_dx = (double)(nt - 1) / (X[nt - 1] - X[0]);
+    for (int c = c_first + lane; c <= c_last; c += 32) {
+        const double ca = fmax(LT[c + 1], x_lo), cb = fmin(LT[c], x_hi);
+        if (!(cb > ca)) continue;
+        const double mc = (LD[c + 1] - LD[c]) / (LT[c + 1] - LT[c]);
+        const double bc = LD[c] - mc * LT[c];
+        int k0 = (int)((ca - X[0]) * inv_dx);
+        k0 = max(0, min(k0, nt - 2));
+        while (k0 > 0 && X[k0] > ca) --k0;
+        while (k0 < nt - 2 && X[k0 + 1] <= ca) ++k0;
+        for (int k = k0; k < nt - 1 && X[k] < cb; ++k) {
+            const double x1 = fmax(ca, X[k]), x2 = fmin(cb, X[k + 1]);
+            if (!(x2 > x1)) continue;
+            acc[ACRO_NR] += pow10_segment(1.0 - mc, -bc, x1, x2);
+            const double idx = 1.0 / (X[k + 1] - X[k]);
+#pragma unroll
+            for (int r = 0; r < ACRO_NR; ++r) {
+                const double mr = (Y[r * nt + k + 1] - Y[r * nt + k]) * idx;
+                const double br = Y[r * nt + k + 1] - mr * X[k + 1];
+                acc[r] += pow10_segment(mr + 1.0 - mc, br - bc, x1, x2);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r <= ACRO_NR; ++r) acc[r] = warp_sum(acc[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) st |= __shfl_xor_sync(0xffffffffu, st, o);
+    if (lane != 0) return;
+    double A[81], Mp[81], Md[81];
+    for (int i = 0; i < 81; ++i) { Mp[i] = 0.0; Md[i] = 0.0; }
+    // mpdi[i][j] = sum_r pref_r(i,j) I_r with I_r = int_{Tmin}^{Tmax} Gamma_r/|dT/dt| dT > 0: the reference integrates
+    // pref*Gamma/(dT/dt) from log Tmax DOWN to log Tmin with dT/dt < 0, which is the same number (nucl.py:563-570,613)
+    for (int r = 0; r < ACRO_NR; ++r) {
+        const int j = kReacInit[r];
+        bool in_final = false;
+        for (int i = 0; i < 9; ++i)
+            if (kReacFinal[r][i] != 0) { Mp[i * 9 + j] += kReacFinal[r][i] * acc[r]; if (i == j) in_final = true; }
+        if (!in_final) Mp[j * 9 + j] += -acc[r];
+    }
+    const double In = (kHbar / kTauN) * acc[ACRO_NR], It = (kHbar / kTauT) * acc[ACRO_NR];
+    Md[0 * 9 + 0] = -In; Md[1 * 9 + 0] = In;    // n -> p
+    Md[3 * 9 + 3] = -It; Md[4 * 9 + 3] = It;    // t -> He3
+    for (int i = 0; i < 81; ++i) A[i] = Mp[i] + Md[i];
+    if (mpdi_out) for (int i = 0; i < 81; ++i) mpdi_out[(int64_t)pt * 81 + i] = Mp[i];
+    if (mdcy_out) for (int i = 0; i < 81; ++i) mdcy_out[(int64_t)pt * 81 + i] = Md[i];
+    int bad = 0;
+    if (Yf_out) {
+        double Yf[27];
+        apply_transfer(A, pt_t_at_tmax[pt], t.Y0, nullptr, Yf, &bad);
+        for (int i = 0; i < 27; ++i) Yf_out[(int64_t)pt * 27 + i] = Yf[i];
+    }
+    if (bad) st |= ACRO_ST_NONFINITE;
+    if (pt_e0 && (double)(int)pt_e0[pt] > 1e3) st |= ACRO_ST_E0_ABOVE_GEV;
+    if (status_out) status_out[pt] = st;
+}
+
+__global__ void __launch_bounds__(64) transfer_kernel(int n, const double* __restrict__ mpdi, const double* __restrict__ mdcy,
+                                                      const double* __restrict__ factor, const double* __restrict__ t_at_tmax,
+                                                      double* __restrict__ expm_out, double* __restrict__ Yf_out,
+                                                      int32_t* __restrict__ status, DeviceTables t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double A[81], Yf[27];
+    const double f = factor ? factor[i] : 1.0;
+    for (int k = 0; k < 81; ++k) A[k] = f * mpdi[(int64_t)i * 81 + k] + mdcy[(int64_t)i * 81 + k];
+    int bad = 0;
+    apply_transfer(A, t_at_tmax[i], t.Y0, expm_out ? expm_out + (int64_t)i * 81 : nullptr, Yf, &bad);
+    for (int k = 0; k < 27; ++k) Yf_out[(int64_t)i * 27 + k] = Yf[k];
+    if (status) status[i] = bad ? ACRO_ST_NONFINITE : 0;
+}
+
+// total rates for arbitrary (E,T) pairs -> out[n][3]
+__global__ void total_rates_kernel(int n, const double* __restrict__ E, const double* __restrict__ T, double* __restrict__ out,
+                                   DeviceTables t, acro_params_t p, DirectRateItem* __restrict__ items, int* __restrict__ item_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RateEval r = eval_rates(E[i], T[i], t, p);
+    out[3 * (int64_t)i] = r.g_ph; out[3 * (int64_t)i + 1] = r.g_el; out[3 * (int64_t)i + 2] = r.g_el;
+    if (r.direct) {
+        const int k = atomicAdd(item_count, 1);
+        DirectRateItem it;
+        it.g_index = 3 * (int64_t)i; it.ne = 1; it.kind = r.direct; it.E = E[i]; it.T = T[i];
+        items[k] = it;
+    }
+}
+
+// DFMA throughput micro-benchmark: 8 independent chains per thread
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------------
+static int sm_count() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    return n;
+}
+
+cudaError_t launch_rates(const acro_batch_t& b, const acro_out_t& o, const DeviceTables& t, const acro_params_t& p,
+                         DirectRateItem* items, int* item_count, int* status_sys, cudaStream_t st, LaunchCounters& lc) {
+    if (b.n_sys_energy_total == 0) return cudaSuccess;
+    const int64_t blocks = (b.n_sys_energy_total + 255) / 256;
+    rates_kernel<<<(unsigned)blocks, 256, 0, st>>>(b, o.G, t, p, items, item_count, status_sys);
+    lc.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_direct_rates(const DeviceTables& t, const acro_params_t& p, double* G, const DirectRateItem* items,
+                                const int* item_count, int64_t max_items, cudaStream_t st, LaunchCounters& lc) {
+    (void)t;
+    if (max_items == 0) return cudaSuccess;
+    int64_t blocks = (max_items + 3) / 4;                       // 4 warps per block, grid-stride over the list
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    direct_rates_kernel<<<(unsigned)blocks, 128, 0, st>>>(G, items, item_count, p);
+    lc.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const acro_params_t& p, double* Kws,
+                           cudaStream_t st, LaunchCounters& lc) {
+    if (b.n_pairs_total == 0) return cudaSuccess;
+    const int64_t blocks = (b.n_pairs_total + 127) / 128;
+    switch (p.quad_order) {
+        case 16: kernels_kernel<16><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
+        case 32: kernels_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
+        case 96: kernels_kernel<96><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
+        default: kernels_kernel<64><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
+    }
+    lc.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_solve_pdi(const acro_batch_t& b, const acro_out_t& o, const DeviceTables& t, const acro_params_t& p,
+                             const double* Kws, cudaStream_t st, LaunchCounters& lc) {
+    (void)t;
+    if (b.n_systems == 0) return cudaSuccess;
+    const int stride = 5 * b.ne_max;                           // doubles per warp
+    int wpb = 4;
+    while (wpb > 1 && (size_t)wpb * stride * sizeof(double) > 200 * 1024) wpb >>= 1;
+    const size_t smem = (size_t)wpb * stride * sizeof(double);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(solve_pdi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int blocks = (b.n_systems + wpb - 1) / wpb;
+    solve_pdi_kernel<<<blocks, wpb * 32, smem, st>>>(b, o.G, o.F, o.pdi, Kws, p, stride);
+    lc.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_matrix(int n_points, const int32_t* pt_nt, const int32_t* pt_sys_off, const double* sys_T,
+                          const double* pdi, const double* T_lo, const double* pt_t_at_tmax, const int* status_sys,
+                          const double* pt_e0, int nt_max, double* mpdi, double* mdcy, double* Yf, int32_t* status,
+                          const DeviceTables& t, const acro_params_t& p, cudaStream_t st, LaunchCounters& lc) {
+    if (n_points == 0) return cudaSuccess;
+    const size_t smem = (size_t)(ACRO_NR + 1) * nt_max * sizeof(double);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    matrix_kernel<<<n_points, 32, smem, st>>>(n_points, pt_nt, pt_sys_off, sys_T, pdi, T_lo, pt_t_at_tmax, status_sys, pt_e0,
+                                              mpdi, mdcy, Yf, status, t, p);
+    lc.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transfer(int n, const double* mpdi, const double* mdcy, const double* factor, const double* t_at_tmax,
+                            double* expm_out, double* Yf, int32_t* status, const DeviceTables& t, cudaStream_t st,
+                            LaunchCounters& lc) {
+    if (n == 0) return cudaSuccess;
+    transfer_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, mpdi, mdcy, factor, t_at_tmax, expm_out, Yf, status, t);
+    lc.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_total_rates(int n, const double* E, const double* T, double* out, const DeviceTables& t,
+                               const acro_params_t& p, DirectRateItem* items, int* item_count, cudaStream_t st,
+                               LaunchCounters& lc) {
+    if (n == 0) return cudaSuccess;
+    total_rates_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, E, T, out, t, p, items, item_count);
+    lc.launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_direct_rates(t, p, out, items, item_count, n, st, lc);
+}
+
+cudaError_t launch_unpack_kernels(const double* Kws, int64_t n_pairs_total, int64_t k_off, int ne, double* K_dense,
+                                  cudaStream_t st, LaunchCounters& lc) {
+    const int n = 5 * ne * ne;
+    unpack_kernels_kernel<<<(n + 255) / 256, 256, 0, st>>>(Kws, n_pairs_total, k_off, ne, K_dense);
+    lc.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t run_dfma_benchmark(double* tflops, LaunchCounters& lc) {
+    const int blocks = sm_count() * 8, threads = 256, iters = 1 << 16;
+    double* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(double) * blocks * threads);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a);
+        dfma_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+        lc.launches++;
+    }
+    e = cudaGetLastError();
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return e;
+}
+
+}  // namespace acro

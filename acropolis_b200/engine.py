@@ -1,0 +1,374 @@
+"""Batched engine: turns a list of model points into the ragged batch of include/acropolis_b200.h, owns the device
+buffers (torch tensors) and calls the C ABI.  One ``Engine`` per (device, input tables).
+
+This is the B200 replacement of the body of ``AbstractModel._pdi_matrix`` (reference models.py:112-130) for MANY
+models at once; ``acropolis_b200.models`` / ``.scans`` / ``.cascade`` / ``.nucl`` are thin views onto it.
+PyTorch is used for device memory, streams and pinned staging only."""
+import ctypes as C
+from math import log, log10
+
+import numpy as np
+import torch
+
+from acropolis_b200 import _lib
+import acropolis_b200.params as params
+import acropolis_b200.flags as flags
+from acropolis_b200.db import import_data_from_db
+
+
+class PointSpec(object):
+    """Inputs of one model point (everything ``NuclearReactor``/``MatrixGenerator`` read from the model)."""
+    __slots__ = ("E0", "E_grid", "T", "S0", "sc_mode", "sc", "sc_E", "t_at_tmax")
+
+    def __init__(self, E0, E_grid, T, S0, t_at_tmax, sc_mode=_lib.SC_NONE, sc=None, sc_E=None):
+        self.E0 = float(E0)
+        self.E_grid = np.ascontiguousarray(E_grid, dtype=np.float64)
+        self.T = np.ascontiguousarray(T, dtype=np.float64)
+        self.S0 = np.ascontiguousarray(S0, dtype=np.float64).reshape(len(self.T), 3)
+        self.t_at_tmax = float(t_at_tmax)
+        self.sc_mode = sc_mode
+        self.sc = sc        # SEPARABLE: [NT,3]; DENSE: [NT,3,NE]
+        self.sc_E = sc_E    # SEPARABLE: [NE,3]
+
+
+def energy_grid(E0):
+    """NE and E_grid exactly as cascade.py:736-745 (same numpy/math expressions => bit-identical grid)."""
+    NE = max(int(log10(E0 / params.Emin) * params.NE_pd), params.NE_min)
+    return np.logspace(log(params.Emin), log(E0), NE, base=np.e)
+
+
+def temperature_grid(Tmin, Tmax):
+    """NT and Tr exactly as nucl.py:473-477."""
+    NT = int(log10(Tmax / Tmin) * params.NT_pd)
+    return np.logspace(log10(Tmin), log10(Tmax), NT)
+
+
+class _Arena(object):
+    """Packs numpy arrays into one pinned host buffer and one device buffer (a single H2D per chunk)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.host = None
+        self.dev = None
+
+    def upload(self, arrays, stream):
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total += (a.nbytes + 255) & ~255
+        total = max(total, 256)
+        if self.host is None or self.host.numel() < total:
+            cap = int(total * 1.25)
+            self.host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            self.dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        hv = self.host.numpy()
+        for a, o in zip(arrays, offs):
+            if a.nbytes:
+                hv[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+        with torch.cuda.stream(stream):
+            self.dev[:total].copy_(self.host[:total], non_blocking=True)
+        base = self.dev.data_ptr()
+        return [base + o for o in offs], total
+
+
+class Engine(object):
+    _cache = {}
+
+    @classmethod
+    def get(cls, ii, device=None):
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        key = (device.index, id(ii), flags.usedb)
+        eng = cls._cache.get(key)
+        if eng is None:
+            eng = cls._cache[key] = cls(ii, device)
+        return eng
+
+    def __init__(self, ii, device):
+        if not torch.cuda.is_available():
+            raise RuntimeError("acropolis_b200: no CUDA device visible; the hot path has no CPU fallback")
+        self.lib = _lib.load()
+        self.ii = ii
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        rdb = import_data_from_db()
+        self._use_db = rdb is not None
+        if rdb is None:   # flags.usedb False or file absent: every rate comes from the direct integrals
+            rdb = np.full((params.Tnum * params.Enum, 2), -200.0)
+        lT, ldT = ii.cosmo_log_tables()
+        Y0 = np.ascontiguousarray(ii.bbn_abundances(), dtype=np.float64)
+        if Y0.shape[1] < 3:   # fewer than 3 abundance columns: pad with the mean column
+            Y0 = np.ascontiguousarray(np.column_stack([Y0] + [Y0[:, :1]] * (3 - Y0.shape[1])))
+        self.ncol = min(ii.bbn_abundances().shape[1], 3)
+        t = _lib.Tables()
+        t.ratedb = rdb.ctypes.data
+        t.ratedb_nT, t.ratedb_nE = params.Tnum, params.Enum
+        t.ratedb_Elog_min, t.ratedb_Elog_max = params.Emin_log, params.Emax_log
+        t.ratedb_Tlog_min, t.ratedb_Tlog_max = params.Tmin_log, params.Tmax_log
+        t.cosmo_log10_T, t.cosmo_log10_abs_dTdt, t.n_cosmo = lT.ctypes.data, ldT.ctypes.data, lT.shape[0]
+        t.eta = float(ii.parameter("eta"))
+        t.Y0 = Y0[:, :3].copy().ctypes.data
+        self._keep = (rdb, lT, ldT, Y0)
+        h = C.c_void_p()
+        rc = self.lib.acro_create(C.byref(h), device.index, C.byref(t), None)
+        if rc != 0:
+            raise RuntimeError("acro_create failed: %s" % self.lib.acro_last_error(None).decode())
+        self.h = h
+        self._arena = _Arena(device)
+        self._ws = None
+        self._params_key = None
+        self.last_stage_ms = np.zeros(4)
+        self.stage_ms_total = np.zeros(4)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.acro_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, self.lib.acro_last_error(self.h).decode()))
+
+    def _sync_params(self):
+        key = (params.quad_order, params.pdi_cell_order, params.Emin, params.approx_zero, params.Ephb_T_max,
+               params.E_EC_max, bool(flags.usedb and self._use_db))
+        if key != self._params_key:
+            p = _lib.Params(*key[:6], int(key[6]), 0)
+            self._check(self.lib.acro_set_params(self.h, C.byref(p)), "acro_set_params")
+            self._params_key = key
+
+    def launch_count(self):
+        return int(self.lib.acro_launch_count(self.h))
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._check(self.lib.acro_measure_fp64_peak(self.h, C.byref(v)), "acro_measure_fp64_peak")
+        return v.value
+
+    # ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def assemble(points):
+        """Concatenate PointSpecs into the flat arrays of acro_batch_t (host side, numpy)."""
+        P = len(points)
+        ne = np.fromiter((len(p.E_grid) for p in points), dtype=np.int32, count=P)
+        nt = np.fromiter((len(p.T) for p in points), dtype=np.int32, count=P)
+        pt_e_off = np.zeros(P, dtype=np.int64)
+        np.cumsum(ne[:-1], out=pt_e_off[1:])
+        pt_sys_off = np.zeros(P, dtype=np.int32)
+        np.cumsum(nt[:-1], out=pt_sys_off[1:])
+        sys_point = np.repeat(np.arange(P, dtype=np.int32), nt)
+        sys_ne = ne[sys_point].astype(np.int64)
+        S = int(sys_point.shape[0])
+        sys_f_off = np.zeros(S, dtype=np.int64)
+        np.cumsum(sys_ne[:-1], out=sys_f_off[1:])
+        sys_k_off = np.zeros(S, dtype=np.int64)
+        tri = sys_ne * (sys_ne + 1) // 2
+        np.cumsum(tri[:-1], out=sys_k_off[1:])
+        modes = {p.sc_mode for p in points}
+        if modes == {_lib.SC_NONE}:
+            sc_mode, sc, sc_E = _lib.SC_NONE, np.zeros(0), np.zeros(0)
+        elif modes <= {_lib.SC_NONE, _lib.SC_SEPARABLE}:
+            sc_mode = _lib.SC_SEPARABLE
+            sc = np.concatenate([p.sc if p.sc_mode else np.zeros((len(p.T), 3)) for p in points]).reshape(-1)
+            sc_E = np.concatenate([p.sc_E if p.sc_mode else np.zeros((len(p.E_grid), 3)) for p in points]).reshape(-1)
+        else:
+            sc_mode, sc_E = _lib.SC_DENSE, np.zeros(0)
+            parts = []
+            for p in points:
+                if p.sc_mode == _lib.SC_DENSE:
+                    parts.append(np.asarray(p.sc, dtype=np.float64).reshape(-1))
+                elif p.sc_mode == _lib.SC_SEPARABLE:
+                    parts.append((p.sc[:, :, None] * p.sc_E.T[None, :, :]).reshape(-1))
+                else:
+                    parts.append(np.zeros(len(p.T) * 3 * len(p.E_grid)))
+            sc = np.concatenate(parts)
+        a = dict(pt_ne=ne, pt_nt=nt, pt_e_off=pt_e_off, pt_sys_off=pt_sys_off,
+                 pt_e0=np.fromiter((p.E0 for p in points), dtype=np.float64, count=P),
+                 pt_t_at_tmax=np.fromiter((p.t_at_tmax for p in points), dtype=np.float64, count=P),
+                 e_grid=np.concatenate([p.E_grid for p in points]),
+                 sys_point=sys_point, sys_T=np.concatenate([p.T for p in points]),
+                 sys_f_off=sys_f_off, sys_k_off=sys_k_off,
+                 s0=np.concatenate([p.S0 for p in points]).reshape(-1),
+                 sc=np.ascontiguousarray(sc, dtype=np.float64), sc_E=np.ascontiguousarray(sc_E, dtype=np.float64))
+        counts = dict(n_points=P, n_systems=S, n_energy_total=int(ne.sum()), n_sys_energy_total=int(sys_ne.sum()),
+                      n_pairs_total=int(tri.sum()), ne_max=int(ne.max()), nt_max=int(nt.max()), sc_mode=sc_mode)
+        return a, counts
+
+    _ORDER = ("pt_ne", "pt_nt", "pt_e_off", "pt_sys_off", "pt_e0", "pt_t_at_tmax", "e_grid", "sys_point", "sys_T",
+              "sys_f_off", "sys_k_off", "s0", "sc", "sc_E")
+
+    @staticmethod
+    def point_cost_bytes(ne, nt):
+        """Workspace bytes one point needs (5 K planes + rate work list)."""
+        return nt * (5 * 8 * (ne * (ne + 1) // 2) + 32 * ne) + 4 * nt + 512
+
+    def chunks(self, points, budget=None):
+        """Greedy split of the point list so that each chunk's workspace fits the budget."""
+        budget = params.workspace_bytes if budget is None else budget
+        out, cur, acc = [], [], 0
+        for i, p in enumerate(points):
+            c = self.point_cost_bytes(len(p.E_grid), len(p.T))
+            if cur and acc + c > budget:
+                out.append(cur)
+                cur, acc = [], 0
+            cur.append(i)
+            acc += c
+        if cur:
+            out.append(cur)
+        return out
+
+    def run(self, points, stages=_lib.STAGE_ALL, want=("Yf", "mpdi", "mdcy", "status"), budget=None, sync=True):
+        """Run the hot path for a list of PointSpecs.  Returns a dict of numpy arrays for the keys in `want`
+        (any of G, F, pdi, mpdi, mdcy, Yf, status), concatenated over points in input order."""
+        self._sync_params()
+        res = {k: [] for k in want}
+        pending = []
+        for idx in self.chunks(points, budget):
+            pending.append(self._run_chunk([points[i] for i in idx], stages, want))
+            if len(pending) > 1:                      # keep one chunk in flight while the next is assembled
+                self._collect(pending.pop(0), res)
+        for pnd in pending:
+            self._collect(pnd, res)
+        return {k: (np.concatenate(v) if v else np.zeros(0)) for k, v in res.items()}
+
+    def _run_chunk(self, pts, stages, want):
+        a, cnt = self.assemble(pts)
+        st = self.stream
+        ptrs, _ = self._arena_for_chunk().upload([a[k] for k in self._ORDER], st)
+        b = _lib.Batch()
+        for k, v in cnt.items():
+            setattr(b, k, v)
+        for k, ptr in zip(self._ORDER, ptrs):
+            setattr(b, k, ptr if a[k].nbytes else None)
+        S, P, NF = cnt["n_systems"], cnt["n_points"], cnt["n_sys_energy_total"]
+        dev = self.device
+        with torch.cuda.stream(st):
+            outs = dict(G=torch.empty(NF * 3, dtype=torch.float64, device=dev),
+                        pdi=torch.empty(S * _lib.NR, dtype=torch.float64, device=dev),
+                        mpdi=torch.empty(P * 81, dtype=torch.float64, device=dev),
+                        mdcy=torch.empty(P * 81, dtype=torch.float64, device=dev),
+                        Yf=torch.empty(P * 27, dtype=torch.float64, device=dev),
+                        status=torch.zeros(P, dtype=torch.int32, device=dev))
+            if "F" in want:
+                outs["F"] = torch.empty(NF * 3, dtype=torch.float64, device=dev)
+            need = int(self.lib.acro_workspace_bytes(self.h, C.byref(b)))
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        o = _lib.Out()
+        for k, t in outs.items():
+            setattr(o, k, t.data_ptr())
+        rc = self.lib.acro_run_batch(self.h, C.byref(b), C.byref(o), self._ws.data_ptr(), self._ws.numel(), stages,
+                                     st.cuda_stream)
+        self._check(rc, "acro_run_batch")
+        host = {}
+        with torch.cuda.stream(st):
+            for k in want:
+                host[k] = torch.empty(outs[k].shape, dtype=outs[k].dtype, pin_memory=True)
+                host[k].copy_(outs[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        return dict(host=host, ev=ev, cnt=cnt, keep=(outs, b, o, a), batch=b)
+
+    def _arena_for_chunk(self):
+        # two arenas alternate so that chunk n+1 can be staged while chunk n is still being read by the GPU
+        if not hasattr(self, "_arenas"):
+            self._arenas, self._arena_i = [_Arena(self.device), _Arena(self.device)], 0
+        self._arena_i ^= 1
+        return self._arenas[self._arena_i]
+
+    def _collect(self, pnd, res):
+        pnd["ev"].synchronize()
+        ms = (C.c_float * 4)()
+        if self.lib.acro_last_stage_ms(self.h, C.byref(ms)) == 0:
+            self.last_stage_ms = np.array(list(ms), dtype=np.float64)
+            self.stage_ms_total += self.last_stage_ms
+        cnt = pnd["cnt"]
+        shapes = dict(Yf=(cnt["n_points"], 9, 3), mpdi=(cnt["n_points"], 9, 9), mdcy=(cnt["n_points"], 9, 9),
+                      status=(cnt["n_points"],), pdi=(cnt["n_systems"], _lib.NR), G=(-1,), F=(-1,))
+        for k, t in pnd["host"].items():
+            res[k].append(t.numpy().reshape(shapes[k]).copy())
+
+    # ------------------------------------------------------------------------------------------------------
+    def kernels_of(self, point, it):
+        """Dense K[5,NE,NE] (planes gg, eg, ge-, ge+, ee) of `point` at temperature index `it` (parity checks)."""
+        self._sync_params()
+        sub = PointSpec(point.E0, point.E_grid, point.T[it:it + 1], point.S0[it:it + 1], point.t_at_tmax)
+        pnd = self._run_chunk([sub], _lib.STAGE_RATES | _lib.STAGE_KERNELS, ("G",))
+        ne = len(point.E_grid)
+        K = torch.empty(5 * ne * ne, dtype=torch.float64, device=self.device)
+        with torch.cuda.stream(self.stream):
+            self._check(self.lib.acro_unpack_kernels(self.h, C.byref(pnd["batch"]), self._ws.data_ptr(), 0, K.data_ptr(),
+                                                     self.stream.cuda_stream), "acro_unpack_kernels")
+        self.stream.synchronize()
+        return K.cpu().numpy().reshape(5, ne, ne), pnd["host"]["G"].numpy().reshape(3, ne).copy()
+
+    def total_rates(self, E, T):
+        """Gamma_X(E,T) for arrays of (E,T) -> [n,3] (SpectrumGenerator._rate_x, cascade.py:721-730)."""
+        self._sync_params()
+        E = np.ascontiguousarray(np.broadcast_arrays(E, T)[0], dtype=np.float64).reshape(-1)
+        T = np.ascontiguousarray(np.broadcast_to(T, E.shape), dtype=np.float64).reshape(-1)
+        n = E.shape[0]
+        dE, dT = torch.from_numpy(E).to(self.device), torch.from_numpy(T).to(self.device)
+        out = torch.empty(n * 3, dtype=torch.float64, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.lib.acro_total_rates(self.h, n, dE.data_ptr(), dT.data_ptr(), out.data_ptr(),
+                                              self.stream.cuda_stream), "acro_total_rates")
+        return out.cpu().numpy().reshape(n, 3)
+
+    def matp(self, T_list, pdi_list, T_lo=None, t_at_tmax=None, want_Yf=False):
+        """MatrixGenerator.get_matp for several points: T_list[p] (NT_p,), pdi_list[p] (NT_p,17)."""
+        self._sync_params()
+        P = len(T_list)
+        nt = np.array([len(t) for t in T_list], dtype=np.int32)
+        off = np.zeros(P, dtype=np.int32)
+        np.cumsum(nt[:-1], out=off[1:])
+        dev = self.device
+        d_nt, d_off = torch.from_numpy(nt).to(dev), torch.from_numpy(off).to(dev)
+        d_T = torch.from_numpy(np.concatenate(T_list).astype(np.float64)).to(dev)
+        d_pdi = torch.from_numpy(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, _lib.NR) for p in pdi_list])
+                                 .reshape(-1)).to(dev)
+        d_lo = torch.from_numpy(np.asarray(T_lo, dtype=np.float64)).to(dev) if T_lo is not None else None
+        d_tt = torch.from_numpy(np.asarray(t_at_tmax if t_at_tmax is not None else np.zeros(P), dtype=np.float64)).to(dev)
+        mpdi = torch.empty(P * 81, dtype=torch.float64, device=dev)
+        mdcy = torch.empty(P * 81, dtype=torch.float64, device=dev)
+        Yf = torch.empty(P * 27, dtype=torch.float64, device=dev)
+        status = torch.zeros(P, dtype=torch.int32, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        rc = self.lib.acro_matp_batch(self.h, P, int(nt.max()), d_nt.data_ptr(), d_off.data_ptr(), d_T.data_ptr(),
+                                      d_pdi.data_ptr(), d_lo.data_ptr() if d_lo is not None else None, d_tt.data_ptr(),
+                                      mpdi.data_ptr(), mdcy.data_ptr(), Yf.data_ptr(), status.data_ptr(),
+                                      self.stream.cuda_stream)
+        self._check(rc, "acro_matp_batch")
+        self.stream.synchronize()
+        out = (mpdi.cpu().numpy().reshape(P, 9, 9), mdcy.cpu().numpy().reshape(P, 9, 9))
+        if want_Yf:
+            return out + (Yf.cpu().numpy().reshape(P, 9, 3), status.cpu().numpy())
+        return out
+
+    def transfer(self, mpdi, mdcy, factor, t_at_tmax, want_expm=False):
+        """Fast-parameter path: Yf[n,9,3] = postd . expm(factor*mpdi + mdcy) . pred . Y0 (scans.py:106-107)."""
+        dev = self.device
+        mpdi = np.ascontiguousarray(mpdi, dtype=np.float64).reshape(-1, 81)
+        n = mpdi.shape[0]
+        d_mp = torch.from_numpy(mpdi.reshape(-1)).to(dev)
+        d_md = torch.from_numpy(np.ascontiguousarray(mdcy, dtype=np.float64).reshape(-1)).to(dev)
+        d_f = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(factor, (n,)), dtype=np.float64)).to(dev)
+        d_t = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(t_at_tmax, (n,)), dtype=np.float64)).to(dev)
+        Yf = torch.empty(n * 27, dtype=torch.float64, device=dev)
+        ex = torch.empty(n * 81, dtype=torch.float64, device=dev) if want_expm else None
+        status = torch.zeros(n, dtype=torch.int32, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        rc = self.lib.acro_transfer_batch(self.h, n, d_mp.data_ptr(), d_md.data_ptr(), d_f.data_ptr(), d_t.data_ptr(),
+                                          ex.data_ptr() if ex is not None else None, Yf.data_ptr(), status.data_ptr(),
+                                          self.stream.cuda_stream)
+        self._check(rc, "acro_transfer_batch")
+        self.stream.synchronize()
+        if want_expm:
+            return Yf.cpu().numpy().reshape(n, 9, 3), ex.cpu().numpy().reshape(n, 9, 9)
+        return Yf.cpu().numpy().reshape(n, 9, 3)

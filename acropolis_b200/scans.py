@@ -1,0 +1,260 @@
+"""Parameter scans: ``ScanParameter`` / ``BufferedScanner`` with the reference's interface (acropolis/scans.py:16-245)
+and result layout (rows ``[scan params sorted by key, 9 mean, 9 high, 9 low]``, scans.py:122-124).
+
+The reference fans the grid out over a ``multiprocessing.Pool`` (scans.py:210-227).  Here the grid is flattened,
+trivial points (E0 <= Emin) are answered on the spot, and all remaining points go through the batched CUDA engine
+in a few launches per stage; with several GPUs the point list is dealt out cost-balanced (cost ~ NT*NE^2) and the
+rows are gathered at the end -- no collective on the hot path.  Two ways to use several GPUs:
+
+* one process, ``perform_scan(devices=[0,1,...])`` (default: every visible device);
+* one process per GPU under ``torchrun``: every rank calls ``perform_scan()``; ranks compute their shard and the
+  rows are all-gathered so every rank returns the full table (``ACROPOLIS_B200_DIST=0`` disables this)."""
+from functools import partial
+import os
+from time import time
+
+import numpy as np
+
+from acropolis_b200.pprint import print_info, print_error
+from acropolis_b200.models import AbstractModel
+from acropolis_b200.engine import Engine
+import acropolis_b200.params as params
+
+
+class ScanParameter(object):
+
+    def __init__(self, ivalue, fvalue, num, spacing="log", fast=False):
+        self._sInitialValue = ivalue
+        self._sFinalValue = fvalue
+        self._sSpacingMode = spacing
+        self._sFastParameter = fast
+        self._sNumPoints = num
+
+    def get_range(self):
+        if self._sSpacingMode == "log":
+            return np.logspace(self._sInitialValue, self._sFinalValue, self._sNumPoints)
+        elif self._sSpacingMode == "lin":
+            return np.linspace(self._sInitialValue, self._sFinalValue, self._sNumPoints)
+
+    def is_fast(self):
+        return self._sFastParameter
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sharding helpers (host logic; covered by gloo world_size-2 tests)
+# ---------------------------------------------------------------------------------------------------------------
+def point_cost(ne, nt):
+    """Relative cost of one point: NT * NE(NE+1)/2 kernel entries (SURVEY.md section 6 cost model)."""
+    return float(nt) * ne * (ne + 1) / 2.0
+
+
+def shard_indices(costs, n_shards):
+    """Deal items to shards, heaviest first, always to the currently lightest shard (LPT).  Returns a list of
+    index arrays (each sorted ascending) that partition range(len(costs))."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-costs, kind="stable")
+    load = np.zeros(n_shards)
+    shards = [[] for _ in range(n_shards)]
+    for i in order:
+        k = int(np.argmin(load))
+        shards[k].append(int(i))
+        load[k] += costs[i]
+    return [np.array(sorted(s), dtype=np.int64) for s in shards]
+
+
+def _dist_world():
+    if os.environ.get("ACROPOLIS_B200_DIST", "1") == "0":
+        return None
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def gather_rows(local_idx, local_rows, n_total, width, dist=None):
+    """All-gather per-rank result rows into the full [n_total, width] table (every rank gets it)."""
+    dist = _dist_world() if dist is None else dist
+    full = np.zeros((n_total, width))
+    if dist is None:
+        full[local_idx] = local_rows
+        return full
+    import torch
+    ws = dist.get_world_size()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    n_loc = torch.tensor([len(local_idx)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(ws)]
+    dist.all_gather(counts, n_loc)
+    n_max = int(max(int(c.item()) for c in counts))
+    buf = torch.zeros((n_max, width + 1), dtype=torch.float64, device=dev)
+    if len(local_idx):
+        buf[:len(local_idx), 0] = torch.from_numpy(np.asarray(local_idx, dtype=np.float64)).to(dev)
+        buf[:len(local_idx), 1:] = torch.from_numpy(np.asarray(local_rows, dtype=np.float64).reshape(-1, width)).to(dev)
+    bufs = [torch.zeros_like(buf) for _ in range(ws)]
+    dist.all_gather(bufs, buf)
+    for c, b in zip(counts, bufs):
+        n = int(c.item())
+        if n:
+            b = b[:n].cpu().numpy()
+            full[b[:, 0].astype(np.int64)] = b[:, 1:]
+    return full
+
+
+def run_models(models, devices=None, want_matp=False):
+    """Final abundances of many models at once -> Yf[N, 9, ncol]  (N x ``run_disintegration``, reference
+    models.py:43-91).  Trivial models (E0 <= Emin) get the post-decayed input abundances.  With ``want_matp`` the
+    per-model (mpdi, mdcy) are returned as well (None for trivial models)."""
+    N = len(models)
+    if N == 0:
+        return np.zeros((0, 9, 3))
+    ncol = models[0]._sII.bbn_abundances().shape[1]
+    Yf = np.zeros((N, 9, ncol))
+    matp = [None] * N
+    work = []
+    for i, m in enumerate(models):
+        if m.is_trivial():
+            Yf[i] = m._squeeze_decays(m._sII.bbn_abundances())
+        else:
+            work.append(i)
+    if not work:
+        return (Yf, matp) if want_matp else Yf
+    specs = [models[i].point_spec() for i in work]
+    import torch
+    if devices is None:
+        dist = _dist_world()
+        devices = [torch.cuda.current_device()] if dist is not None else list(range(torch.cuda.device_count()))
+    devices = list(devices)[:max(1, len(work))]
+    want = ("Yf", "mpdi", "mdcy", "status") if want_matp else ("Yf", "status")
+    if len(devices) == 1:
+        out = Engine.get(models[work[0]]._sII, devices[0]).run(specs, want=want)
+        parts = [(np.arange(len(work)), out)]
+    else:
+        shards = shard_indices([point_cost(len(s.E_grid), len(s.T)) for s in specs], len(devices))
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(devices)) as ex:
+            futs = [ex.submit(Engine.get(models[work[0]]._sII, d).run, [specs[j] for j in sh], want=want)
+                    for d, sh in zip(devices, shards) if len(sh)]
+            parts = [(sh, f.result()) for sh, f in zip([s for s in shards if len(s)], futs)]
+    for sh, out in parts:
+        for k, j in enumerate(sh):
+            Yf[work[j]] = out["Yf"][k][:, :ncol]
+            if want_matp:
+                matp[work[j]] = (out["mpdi"][k], out["mdcy"][k])
+    return (Yf, matp) if want_matp else Yf
+
+
+class BufferedScanner(object):
+
+    def __init__(self, model, **kwargs):
+        self._sModelClass = model.func if type(model) is partial else model
+        if not issubclass(self._sModelClass, AbstractModel):
+            print_error(self._sModelClass.__name__ + " is not a subclass of AbstractModel",
+                        "acropolis_b200.scans.BufferedScanner.__init__")
+        self._sModel = model
+        self._sFixed = {}   # fixed parameters
+        self._sScanp = {}   # scan parameters
+        self._sNP = 0
+        self._sNP_fast = 0
+        self._sFast_id = None
+        self._parse_arguments(**kwargs)
+        self._sScanp_id = list(self._sScanp.keys())
+
+    def _parse_arguments(self, **kwargs):
+        for key, param in kwargs.items():
+            if isinstance(param, ScanParameter):
+                self._sNP += 1
+                self._sScanp[key] = param.get_range()
+                if param.is_fast():
+                    self._sNP_fast += 1
+                    self._sFast_id = key
+            else:
+                self._sFixed[key] = param
+        if self._sNP_fast > 1 or self._sNP != 2:
+            print_error("The class BufferedScanner only supports 2d parameter scans with <= 1 fast parameters!",
+                        "acropolis_b200.scans.BufferedScanner._parse_arguments")
+
+    def _rescale_matp_buffer(self, buffer, factor):
+        return (factor * buffer[0], buffer[1])
+
+    def _build(self, scanp_set):
+        fullp = dict(scanp_set)
+        fullp.update(self._sFixed)
+        return self._sModel(**fullp)
+
+    @staticmethod
+    def _row(scanp_set, Yb):
+        return [*[scanp_set[key] for key in sorted(scanp_set)], *Yb.transpose().reshape(Yb.size)]
+
+    def scan_points(self):
+        """The flattened list of parameter dicts in the reference's order (scans.py:193-208)."""
+        key1, key2 = self._sScanp_id
+        if self._sNP_fast == 0:
+            return [{key1: v1, key2: v2} for v1 in self._sScanp[key1] for v2 in self._sScanp[key2]]
+        keyp = key1 if key1 != self._sFast_id else key2
+        return [{keyp: vp, self._sFast_id: vf} for vp in self._sScanp[keyp] for vf in self._sScanp[self._sFast_id]]
+
+    def perform_scan(self, cores=1, devices=None):
+        """``cores`` is accepted for compatibility (the reference's Pool size); the work runs on the GPU(s)."""
+        assert self._sNP_fast <= 1 and self._sNP == 2
+        start_time = time()
+        print_info("Running scan for {} on the GPU.".format(self._sModelClass.__name__),
+                   "acropolis_b200.scans.BufferedScanner.perform_scan", verbose_level=3)
+        pts = self.scan_points()
+        dist = _dist_world()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+        if self._sNP_fast == 0:
+            rows = self._scan_plain(pts, rank, world, devices)
+        else:
+            rows = self._scan_fast(pts, rank, world, devices)
+        print_info("Finished after {:.1f}min.".format((time() - start_time) / 60),
+                   "acropolis_b200.scans.BufferedScanner.perform_scan", verbose_level=3)
+        return rows
+
+    # -- no fast parameter: every point is a full computation (scans.py:110-124) -------------------------------
+    def _scan_plain(self, pts, rank, world, devices):
+        N = len(pts)
+        mine = np.arange(N)
+        if world > 1:   # cheap cost proxy before any model is built: the E0-dependent grid size is not known here,
+            mine = np.arange(rank, N, world)   # so deal points round-robin (neighbouring points cost the same)
+        models = [self._build(pts[i]) for i in mine]
+        Yf = run_models(models, devices=devices)
+        rows = np.array([self._row(pts[i], Yf[k]) for k, i in enumerate(mine)]).reshape(len(mine), -1)
+        width = 2 + Yf.shape[1] * Yf.shape[2]
+        return gather_rows(mine, rows, N, width) if world > 1 else rows
+
+    # -- one fast parameter: full computation for the first fast value, rescaled mpdi for the rest (scans.py:127-176)
+    def _scan_fast(self, pts, rank, world, devices):
+        fast = self._sScanp[self._sFast_id]
+        nf = len(fast)
+        n_slow = len(pts) // nf
+        slow = np.arange(n_slow) if world == 1 else np.arange(rank, n_slow, world)
+        models = [[self._build(pts[s * nf + f]) for f in range(nf)] for s in slow]
+        # the first fast value whose model is non-trivial supplies the buffer (reference: matpb stays None before)
+        lead = [next((f for f in range(nf) if not row[f].is_trivial()), None) for row in models]
+        lead_models = [row[f] for row, f in zip(models, lead) if f is not None]
+        Yl, matp = run_models(lead_models, devices=devices, want_matp=True) if lead_models else (None, [])
+        it = iter(matp)
+        bufs = [next(it) if f is not None else None for f in lead]
+        ncol = models[0][0]._sII.bbn_abundances().shape[1] if models else 3
+        Yf = np.zeros((len(slow), nf, 9, ncol))
+        jobs = []   # (row, f, mpdi, mdcy, factor, t_at_tmax)
+        for r, row in enumerate(models):
+            for f, m in enumerate(row):
+                if bufs[r] is None or f < lead[r] or m.is_trivial():
+                    # before the buffer exists the reference runs the model itself: trivial by construction
+                    Yf[r, f] = m._squeeze_decays(m._sII.bbn_abundances()) if m.is_trivial() else np.nan
+                else:
+                    m.set_matp_buffer(self._rescale_matp_buffer(bufs[r], fast[f] / fast[lead[r]]))
+                    jobs.append((r, f, bufs[r][0], bufs[r][1], fast[f] / fast[lead[r]], m._t_at_tmax()))
+        if jobs:
+            eng = Engine.get(models[0][0]._sII, None if devices is None else list(devices)[0])
+            Y = eng.transfer(np.array([j[2] for j in jobs]), np.array([j[3] for j in jobs]),
+                             np.array([j[4] for j in jobs]), np.array([j[5] for j in jobs]))
+            for (r, f, *_), y in zip(jobs, Y):
+                Yf[r, f] = y[:, :ncol]
+        idx = np.array([s * nf + f for s in slow for f in range(nf)], dtype=np.int64)
+        rows = np.array([self._row(pts[i], Yf[k // nf, k % nf]) for k, i in enumerate(idx)]).reshape(len(idx), -1)
+        width = 2 + 9 * ncol
+        return gather_rows(idx, rows, len(pts), width) if world > 1 else rows
