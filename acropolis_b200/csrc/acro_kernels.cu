@@ -510,12 +510,28 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
         if (!(hi > y0)) continue;
         const double ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
         const double bs = lnF[c + 1] - ms * y1;
-        const double h = 0.5 * (hi - y0), m = 0.5 * (hi + y0);
         const double Elo = E[c];
+        // integrand = exp((ms+1) y + bs) * sigma(e^y).  Where the exponential factor changes by more than e^0.5 over the
+        // cell (e.g. next to a floored spectrum value) integrate in v = exp(kap (y - y_big)) from the large end: exact
+        // for constant sigma at any steepness; otherwise plain Gauss-Legendre in y.
+        const double kap = ms + 1.0, z = kap * (hi - y0);
+        const bool steep = fabs(z) > 0.5;
+        const double h = 0.5 * (hi - y0), m = 0.5 * (hi + y0);
+        const double yb = (z > 0.0) ? hi : y0;
+        const double vlo = steep ? exp(-fabs(z)) : 0.0;
+        const double pref = steep ? 0.5 * (1.0 - vlo) / fabs(kap) * exp(fma(kap, yb, bs)) : 0.0;
+        const double ikap = 1.0 / kap;
         for (int k = 0; k < nq; ++k) {
-            const double y  = fma(h, qx[k], m);
+            double y, fe;
+            if (steep) {
+                const double v = fma(0.5 * (1.0 - vlo), 1.0 + qx[k], vlo);
+                y  = fma(log(v), ikap, yb);
+                fe = qw[k] * pref;
+            } else {
+                y  = fma(h, qx[k], m);
+                fe = qw[k] * h * exp(fma(kap, y, bs));
+            }
             const double Ev = exp(y);
-            const double fe = qw[k] * h * exp(fma(ms, y, bs)) * Ev;
 #pragma unroll
             for (int r = 0; r < ACRO_NR; ++r)
                 if (kEth[r] <= Elo) acc[r] = fma(fe, cross_section_mb(r + 1, Ev, y), acc[r]);

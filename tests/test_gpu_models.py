@@ -1,0 +1,146 @@
+"""The reference-facing Python surface on the GPU: models, SpectrumGenerator / NuclearReactor / MatrixGenerator views,
+BufferedScanner (plain and fast-parameter scans), and the reference's own stored convergence rows."""
+from functools import partial
+
+import numpy as np
+import pytest
+
+from conftest import golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _quiet():
+    import acropolis_b200.flags as flags
+    flags.verbose = False
+    yield
+
+
+def test_decay_model_cfg1(gpu_engine):
+    """BASELINE config 1: ./decay 10 1e5 10 1e-10 0 1."""
+    from acropolis_b200.models import DecayModel
+    z = golden("cfg1_decay.npz")
+    Yf = DecayModel(10., 1e5, 10., 1e-10, 0., 1.).run_disintegration()
+    assert Yf.shape == (9, 3)
+    assert relerr(Yf, z["Yf"], 1e-30) < 1e-4
+    # SURVEY 8(c) known answers (mean column)
+    assert Yf[2, 0] == pytest.approx(1.83746573e-05, rel=1e-4) and Yf[6, 0] == pytest.approx(8.10470514e-15, rel=1e-4)
+
+
+def test_annihilation_model_cfg2(gpu_engine):
+    from acropolis_b200.models import AnnihilationModel
+    z = golden("cfg2_annih.npz")
+    Yf = AnnihilationModel(10., 1e-25, 0., 0., 1., 0.).run_disintegration()
+    assert relerr(Yf, z["Yf"], 1e-30) < 5e-4   # reference T-quadrature noise, see tests/test_oracle.py
+    assert relerr(Yf[[1, 2, 4, 5, 7]], z["Yf"][[1, 2, 4, 5, 7]], 1e-30) < 1e-4
+
+
+def test_trivial_model_below_threshold(gpu_engine):
+    from acropolis_b200.models import DecayModel
+    m = DecayModel(2.0, 1e5, 10., 1e-10, 0., 1.)      # E0 = 1 MeV <= Emin (models.py:65-71)
+    Y0 = m._sII.bbn_abundances()
+    Yf = m.run_disintegration()
+    assert Yf[0, 0] == 0 and Yf[1, 0] == Y0[0, 0] + Y0[1, 0] and Yf[7, 0] == Y0[7, 0] + Y0[8, 0]
+
+
+def test_user_subclass_scalar_hooks(gpu_engine):
+    """A user model that overrides scalar hooks goes through the generic (dense SC) path and still matches."""
+    from acropolis_b200.models import DecayModel
+    z = golden("decay_ee.npz")
+
+    class MyDecay(DecayModel):
+        def _source_photon_c(self, E, T):
+            return DecayModel._source_photon_c(self, E, T)
+
+    Yf = MyDecay(30., 1e6, 10., 1e-9, 1., 0.).run_disintegration()
+    Yv = DecayModel(30., 1e6, 10., 1e-9, 1., 0.).run_disintegration()
+    assert relerr(Yf, Yv, 1e-30) < 1e-12 and relerr(Yf, z["Yf"], 1e-30) < 1e-4
+
+
+def test_spectrum_generator_view(gpu_engine):
+    from acropolis_b200.models import DecayModel
+    from acropolis_b200.cascade import SpectrumGenerator
+    z = golden("cfg1_decay.npz")
+    m = DecayModel(10., 1e5, 10., 1e-10, 0., 1.)
+    sg = SpectrumGenerator(m._sII)
+    T = float(z["T"][20])
+    sol = sg.get_spectrum(m._sE0, m._sS0, m._sSc, T, allX=True)
+    assert sol.shape == (4, 62) and np.array_equal(sol[0], z["E_grid"])
+    assert relerr(sol[1:], z["F"][20]) < 1e-5
+    assert sg.get_spectrum(m._sE0, m._sS0, m._sSc, T).shape == (2, 62)
+    assert sg.rate_photon(m._sE0, T) == pytest.approx(float(z["rate_photon_E0"][20]), rel=1e-11)
+    E, G, K = sg.get_kernels(m._sE0, T)
+    assert relerr(K, z["K_it20"]) < 1e-5 and relerr(G, z["G"][20]) < 1e-11
+
+
+def test_nuclear_reactor_and_matrix_generator_views(gpu_engine):
+    from acropolis_b200.models import DecayModel
+    from acropolis_b200.nucl import NuclearReactor, MatrixGenerator
+    z = golden("cfg1_decay.npz")
+    m = DecayModel(10., 1e5, 10., 1e-10, 0., 1.)
+    Tr, grids = NuclearReactor(m._sS0, m._sSc, m._sTrg, m._sE0, m._sII).get_pdi_grids()
+    assert np.array_equal(Tr, z["T"]) and sorted(grids) == list(range(1, 18))
+    pdi = np.column_stack([grids[r] for r in range(1, 18)])
+    assert relerr(pdi, z["pdi"], 1e-100) < 1.5e-3
+    mg = MatrixGenerator(Tr, grids, m._sII)
+    mpdi, mdcy = mg.get_final_matp()
+    assert relerr(mdcy, z["mdcy"], 1e-100) < 1e-6 and relerr(mpdi, z["mpdi"], 1e-100) < 1e-3
+    Ts, (all_mpdi, all_mdcy) = mg.get_all_matp()
+    assert all_mpdi.shape == (40, 9, 9) and np.allclose(all_mpdi[0], mpdi, rtol=1e-12) and np.all(all_mpdi[-1] == 0)
+
+
+def test_scan_decay_5x5(gpu_engine):
+    """cfg3 sub-grid: same log ranges as the 200x200 scan, against the reference's multiprocessing scan."""
+    from acropolis_b200.models import DecayModel
+    from acropolis_b200.scans import BufferedScanner, ScanParameter
+    z = golden("scan_decay_5x5.npz")
+    rows = BufferedScanner(DecayModel, mphi=ScanParameter(0, 3, 5), tau=ScanParameter(3, 10, 5), temp0=10., n0a=1e-10,
+                           bree=0., braa=1.).perform_scan(cores=-1)
+    ref = z["rows"]
+    assert rows.shape == ref.shape == (25, 29)
+    assert np.array_equal(rows[:, :2], ref[:, :2])
+    assert relerr(rows[:, 2:], ref[:, 2:], 1e-30) < 1e-4
+
+
+def test_scan_fast_parameter(gpu_engine):
+    from acropolis_b200.models import DecayModel, AnnihilationModel
+    from acropolis_b200.scans import BufferedScanner, ScanParameter
+    z = golden("scan_fast.npz")
+    rows = BufferedScanner(DecayModel, mphi=ScanParameter(0.1, 1.6, 4), tau=1e7, temp0=10.,
+                           n0a=ScanParameter(-14, -3, 8, fast=True), bree=0., braa=1.).perform_scan(cores=4)
+    assert rows.shape == z["decay_rows"].shape and np.array_equal(rows[:, :2], z["decay_rows"][:, :2])
+    assert relerr(rows[:, 2:], z["decay_rows"][:, 2:], 1e-30) < 2e-4
+    rows = BufferedScanner(partial(AnnihilationModel, omegah2=0.12), mchi=ScanParameter(0.5, 1.2, 2), a=0.,
+                           b=ScanParameter(-23, -10, 6, fast=True), tempkd=1., bree=1., braa=0.).perform_scan()
+    assert rows.shape == z["annih_rows"].shape and np.array_equal(rows[:, :2], z["annih_rows"][:, :2])
+    assert relerr(rows[:, 2:], z["annih_rows"][:, 2:], 1e-30) < 5e-4
+
+
+def test_reference_convergence_rows(gpu_engine):
+    """The reference's only stored known answers (tools/data/{NE,NT}_pd_{decay,annih}.dat, 98 rows of Y_D mean/high/low
+    for `decay 50 1e5 10 1e-8 0 1` and `annihilation 10 1e-24 0 0 1 0`), at resolutions up to NE_pd=500 / NT_pd=200 --
+    the full-size configurations (NE up to 610, NT up to 800), all in one batch."""
+    import acropolis_b200.params as params
+    from acropolis_b200.models import DecayModel, AnnihilationModel
+    from acropolis_b200.scans import run_models
+    z = golden("reference_convergence_rows.npz")
+    old = (params.NE_pd, params.NT_pd)
+    specs, refs = [], []
+    try:
+        for key, cls, args in (("decay", DecayModel, (50., 1e5, 10., 1e-8, 0., 1.)),
+                               ("annih", AnnihilationModel, (10., 1e-24, 0., 0., 1., 0.))):
+            for which in ("NE", "NT"):
+                for row in z["%s_pd_%s" % (which, key)]:
+                    params.NE_pd, params.NT_pd = (int(row[0]), 50) if which == "NE" else (150, int(row[0]))
+                    m = cls(*args)
+                    specs.append(m.point_spec())
+                    refs.append(row[1:4])
+    finally:
+        params.NE_pd, params.NT_pd = old
+    out = gpu_engine.run(specs, want=("Yf", "status"))
+    Y_D = out["Yf"][:, 2, :]
+    refs = np.array(refs)
+    assert len(refs) == 98
+    # the stored rows have 6 significant digits; the reference's own quadrature noise on Y_D is ~1e-5 relative
+    assert np.max(np.abs(Y_D / refs - 1)) < 3e-5

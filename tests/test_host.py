@@ -1,0 +1,228 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, the host-side mirror of the reference
+interface (input tables, model hooks, grids, scan bookkeeping, sharding) reproduces the reference's numbers, and the
+product path refuses to run without the CUDA device/library."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden, relerr
+
+
+@pytest.fixture(autouse=True)
+def _quiet():
+    import acropolis_b200.flags as flags
+    flags.verbose = False
+    yield
+
+
+def test_library_exports_every_declared_symbol():
+    from acropolis_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "acropolis_b200.h")).read()
+    declared = set(re.findall(r"\b(acro_[a-z0-9_]+)\s*\(", hdr)) - {"acro_batch_t", "acro_out_t"}
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.acro_abi_version() == 1
+    p = _lib.Params()
+    lib.acro_default_params(p)
+    assert (p.quad_order, p.pdi_cell_order, p.Emin, p.approx_zero, p.Ephb_T_max, p.E_EC_max, p.use_db) == \
+        (64, 8, 1.5, 1e-200, 200.0, 10.0, 1)
+
+
+def test_library_is_built_for_sm_100a():
+    from acropolis_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    """The product never imports oracle/, and the engine refuses to start without a CUDA device."""
+    import torch
+    pkg = os.path.join(ROOT, "acropolis_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "pyoracle" not in src and "liboracle" not in src and "acro_oracle" not in src, f
+    if not torch.cuda.is_available():
+        from acropolis_b200.engine import Engine
+        from acropolis_b200.input import shared_input_interface
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            Engine.get(shared_input_interface())
+
+
+def test_input_interface_known_answers():
+    from acropolis_b200.input import shared_input_interface
+    ii = shared_input_interface()
+    k = json.load(open(os.path.join(GOLDEN, "kat_scalars.json")))
+    assert float(ii.parameter("eta")) == k["eta"]
+    assert np.array_equal(ii.bbn_abundances(), np.array(k["Y0"]))
+    for T, v in k["time_of_T"]:
+        assert ii.time(T) == v
+    for t, v in k["T_of_time"]:
+        assert ii.temperature(t) == v
+    for T, v in k["dTdt"]:
+        assert ii.dTdt(T) == v
+    for T, v in k["scale_factor"]:
+        assert ii.scale_factor(T) == v
+    for T, v in k["hubble_rate"]:
+        assert ii.hubble_rate(T) == v
+    assert list(ii.temperature_range()) == k["temperature_range"]
+    Ts = np.array([T for T, _ in k["scale_factor"]])
+    assert np.allclose(ii.scale_factor(Ts), [v for _, v in k["scale_factor"]], rtol=1e-14)
+    with pytest.raises(ValueError):
+        ii.time(1e9)
+
+
+def test_rate_table_conversion():
+    from acropolis_b200.db import import_data_from_db, in_rate_db
+    z = golden("ratedb_spots.npz")
+    db = import_data_from_db()
+    assert db.shape == tuple(z["shape"]) == (750 * 450, 2)
+    assert np.array_equal(db[z["idx"]], z["vals"])
+    assert in_rate_db(0.0, -6.0) and in_rate_db(3.0, -1.0) and not in_rate_db(3.0000001, -2) and not in_rate_db(1, -6.1)
+
+
+DECAY = ["cfg1_decay", "decay_ee", "decay_nemin", "decay_mixed", "decay_lowT", "decay_highT", "decay_big"]
+
+
+@pytest.mark.parametrize("name", DECAY + ["cfg2_annih", "annih_pwave"])
+def test_model_grids_and_sources_match_reference(name):
+    """E grid, T grid (incl. the 39/40 truncation), S0, SC and t(Tmax) as the reference produces them."""
+    from acropolis_b200.models import DecayModel, AnnihilationModel
+    z = golden(name + ".npz")
+    cls = DecayModel if name in DECAY else AnnihilationModel
+    m = cls(*z["ctor"])
+    sp = m.point_spec()
+    assert np.array_equal(sp.E_grid, z["E_grid"]) and np.array_equal(sp.T, z["T"])
+    assert sp.E0 == float(z["E0"]) and sp.t_at_tmax == float(z["t_at_Tmax"])
+    assert tuple(m._sTrg) == tuple(z["Trg"])
+    assert relerr(sp.S0, z["S0"], 1e-300) < 1e-11   # exp(-dt/tau) with dt/tau ~ 700 amplifies one ulp of t(T)
+    NT, NE = len(sp.T), len(sp.E_grid)
+    if sp.sc_mode == 0:
+        assert not np.any(z["SC"])
+    else:
+        SC = sp.sc[:, :, None] * sp.sc_E.T[None, :, :]
+        assert SC.shape == (NT, 3, NE) and relerr(SC, z["SC"], 1e-300) < 1e-11
+        assert np.array_equal(SC == 0, z["SC"] == 0)
+    # the scalar hooks (what user code may call) agree with the vectorised arrays
+    it = NT // 2
+    assert m._sS0[0](sp.T[it]) == pytest.approx(z["S0"][it, 0], rel=1e-13, abs=0)
+    assert m._sSc[0](sp.E_grid[3], sp.T[it]) == pytest.approx(z["SC"][it, 0, 3], rel=1e-13, abs=0)
+    assert np.array_equal(m._pred_matrix(), z["pred"]) and np.array_equal(m._postd_matrix(), z["postd"])
+
+
+def test_hires_grid_sizes():
+    import acropolis_b200.params as params
+    from acropolis_b200.models import DecayModel
+    z = golden("decay_hires_ne60_nt50.npz")
+    old = (params.NE_pd, params.NT_pd)
+    try:
+        params.NE_pd, params.NT_pd = 60, 50
+        sp = DecayModel(*z["ctor"]).point_spec()
+    finally:
+        params.NE_pd, params.NT_pd = old
+    assert np.array_equal(sp.E_grid, z["E_grid"]) and np.array_equal(sp.T, z["T"])
+
+
+def test_scan_bookkeeping():
+    from functools import partial
+    from acropolis_b200.models import DecayModel
+    from acropolis_b200.scans import BufferedScanner, ScanParameter
+    from acropolis_b200.pprint import AcropolisError
+    z = golden("scan_decay_5x5.npz")
+    sc = BufferedScanner(DecayModel, mphi=ScanParameter(0, 3, 5), tau=ScanParameter(3, 10, 5), temp0=10., n0a=1e-10,
+                         bree=0., braa=1.)
+    pts = sc.scan_points()
+    assert len(pts) == 25
+    assert np.array_equal(np.array([[p["mphi"], p["tau"]] for p in pts]), z["rows"][:, :2])
+    zf = golden("scan_fast.npz")
+    sf = BufferedScanner(partial(DecayModel, temp0=10.), mphi=ScanParameter(0.1, 1.6, 4), tau=1e7,
+                         n0a=ScanParameter(-14, -3, 8, fast=True), bree=0., braa=1.)
+    pts = sf.scan_points()
+    assert np.array_equal(np.array([[p["mphi"], p["n0a"]] for p in pts]), zf["decay_rows"][:, :2])
+    assert np.array_equal(ScanParameter(0, 1, 3, spacing="lin").get_range(), np.linspace(0, 1, 3))
+    with pytest.raises(AcropolisError):
+        BufferedScanner(DecayModel, mphi=ScanParameter(0, 3, 5), tau=1e5, temp0=10., n0a=1e-10, bree=0., braa=1.)
+    with pytest.raises(AcropolisError):
+        BufferedScanner(dict, mphi=ScanParameter(0, 3, 5), tau=ScanParameter(3, 10, 5))
+    # trivial rows (E0 <= Emin) need no device: mphi = 1 MeV
+    m = DecayModel(1.0, 1e5, 10., 1e-10, 0., 1.)
+    assert m.is_trivial()
+    row = np.array(sc._row({"mphi": 1.0, "tau": 1e3}, m.run_disintegration()))
+    assert relerr(row[2:], z["rows"][0, 2:], 1e-30) < 1e-15
+
+
+def test_assemble_offsets():
+    from acropolis_b200.engine import Engine, PointSpec
+    rng = np.random.default_rng(0)
+    pts = []
+    for ne, nt in ((10, 3), (17, 5), (33, 2)):
+        pts.append(PointSpec(5.0, np.sort(rng.random(ne)) + 1.5, np.sort(rng.random(nt)), rng.random((nt, 3)), 1.0))
+    a, c = Engine.assemble(pts)
+    assert c["n_points"] == 3 and c["n_systems"] == 10 and c["n_energy_total"] == 60 and c["ne_max"] == 33 and c["nt_max"] == 5
+    assert c["n_sys_energy_total"] == 10 * 3 + 17 * 5 + 33 * 2
+    assert c["n_pairs_total"] == 55 * 3 + 153 * 5 + 561 * 2
+    assert list(a["pt_e_off"]) == [0, 10, 27] and list(a["pt_sys_off"]) == [0, 3, 8]
+    assert list(a["sys_point"]) == [0] * 3 + [1] * 5 + [2] * 2
+    assert list(a["sys_f_off"][:5]) == [0, 10, 20, 30, 47] and a["sys_k_off"][3] == 165 and a["sys_k_off"][4] == 165 + 153
+    assert c["sc_mode"] == 0
+
+
+def test_shard_indices_partition_and_balance():
+    from acropolis_b200.scans import shard_indices, point_cost
+    rng = np.random.default_rng(1)
+    ne = rng.integers(10, 303, size=500)
+    costs = [point_cost(n, 40) for n in ne]
+    for k in (1, 2, 4, 8):
+        sh = shard_indices(costs, k)
+        assert sorted(np.concatenate(sh).tolist()) == list(range(500))
+        loads = np.array([sum(costs[i] for i in s) for s in sh])
+        assert loads.max() / loads.mean() < 1.02
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from acropolis_b200.scans import gather_rows
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, width = 11, 29
+    mine = np.arange(rank, n, world)
+    rows = np.array([[i * 100.0 + c for c in range(width)] for i in mine]).reshape(len(mine), width)
+    full = gather_rows(mine, rows, n, width)
+    q.put((rank, full))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_rows_gloo_world2():
+    """N>1 path of perform_scan: ranks compute interleaved shards, rows are all-gathered (gloo, world_size 2)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    expect = np.array([[i * 100.0 + c for c in range(29)] for i in range(11)])
+    assert np.array_equal(got[0], expect) and np.array_equal(got[1], expect)
+
+
+def test_fsr_shape_matches_scalar_hook():
+    from acropolis_b200.models import DecayModel, _fsr_shape
+    m = DecayModel(30., 1e6, 10., 1e-9, 1., 0.)
+    E = np.array([1.5, 3.0, 14.9, 14.99, 15.0])
+    T = 1e-3
+    ref = np.array([m._source_photon_c(e, T) for e in E])
+    assert np.allclose(_fsr_shape(E, 15.0) * m._source_electron_0(T), ref, rtol=1e-14, atol=0)
+    assert ref[-1] == 0.0
