@@ -176,6 +176,23 @@ int acro_run_batch(acro_handle_t* h, const acro_batch_t* b, const acro_out_t* o,
     return ACRO_OK;
 }
 
+int acro_count_work(acro_handle_t* h, const acro_batch_t* b, int64_t out[4], void* stream) {
+    if (!h || !b || !out) return ACRO_EINVAL;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* d = nullptr;
+    CU(h, cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = launch_count_work(*b, h->params, d, st, h->lc);
+    unsigned long long hv[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hv, d, sizeof(hv), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, ACRO_ECUDA, std::string("acro_count_work: ") + cudaGetErrorString(e));
+    for (int i = 0; i < 4; ++i) out[i] = (int64_t)hv[i];
+    return ACRO_OK;
+}
+
 int acro_last_stage_ms(acro_handle_t* h, float ms[4]) {
     if (!h || !ms) return ACRO_EINVAL;
     if (!h->ev_valid) return fail(h, ACRO_EINVAL, "no batch has been run");

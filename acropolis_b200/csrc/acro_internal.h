@@ -40,6 +40,8 @@ cudaError_t launch_direct_rates(const DeviceTables& t, const acro_params_t& p, d
                                 const int* item_count, int64_t max_items, cudaStream_t st, LaunchCounters& lc);
 cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const acro_params_t& p, double* Kws,
                            cudaStream_t st, LaunchCounters& lc);
+cudaError_t launch_count_work(const acro_batch_t& b, const acro_params_t& p, unsigned long long* out, cudaStream_t st,
+                              LaunchCounters& lc);
 cudaError_t launch_solve_pdi(const acro_batch_t& b, const acro_out_t& o, const DeviceTables& t, const acro_params_t& p,
                              const double* Kws, cudaStream_t st, LaunchCounters& lc);
 cudaError_t launch_matrix(int n_points, const int32_t* pt_nt, const int32_t* pt_sys_off, const double* sys_T,

@@ -355,6 +355,51 @@ __global__ void __launch_bounds__(128) kernels_kernel(acro_batch_t b, double* __
     Kws[4 * np + tid] = k.ee;
 }
 
+// Counts, for the roofline's algorithmic-work figure, the (system, i, j>=i) pairs and how many of them
+// have a non-empty integration range for each of the three thermal integrals -- the same limit tests as
+// eval_kernels, no quadrature.  out[0..3] = pairs, N_a9 (e->gamma), N_a10 (e->e), N_a11 (gamma->e).
+__global__ void __launch_bounds__(128) count_work_kernel(acro_batch_t b, unsigned long long* __restrict__ out, acro_params_t p) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int c9 = 0, c10 = 0, c11 = 0, cp = 0;
+    if (tid < b.n_pairs_total) {
+        const int s  = owner_of(b.sys_k_off, b.n_systems, tid);
+        const int64_t loc = tid - b.sys_k_off[s];
+        const int pt = b.sys_point[s];
+        const int ne = b.pt_ne[pt];
+        const double tn = 2.0 * ne + 1.0;
+        int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+        i = max(0, min(i, ne - 1));
+        while (i > 0 && tri_row_off(i, ne) > loc) --i;
+        while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
+        const int j = i + (int)(loc - tri_row_off(i, ne));
+        const double* eg = b.e_grid + b.pt_e_off[pt];
+        const double E = eg[i], Ep = eg[j], T = b.sys_T[s], xmax = p.Ephb_T_max * T;
+        cp = 1;
+        if (!(Ep < E + kMe)) {
+            const double llim = 0.25 * kMe2 * E / (Ep * Ep - Ep * E);
+            c9 = fmin(fmin(E, Ep - kMe2 / (4.0 * Ep)), xmax) > llim;
+        }
+        if (E != Ep) {
+            const double pf = 0.25 * kMe2 / Ep - E, qf = 0.25 * kMe2 * (Ep - E) / Ep;
+            const double sq = sqrt((0.5 * pf) * (0.5 * pf) - qf);
+            c10 = fmin(fmin(-0.5 * pf + sq, Ep - kMe2 / (4.0 * Ep)), xmax) > (-0.5 * pf - sq);
+        }
+        if (!(Ep < kMe2 / (50.0 * T))) {
+            const double dE = Ep - E, rt = sqrt(E * E - kMe2), den = 4.0 * Ep * dE + kMe2;
+            const double z1 = Ep * (kMe2 - 2.0 * dE * (rt - E)) / den, z2 = Ep * (kMe2 + 2.0 * dE * (rt + E)) / den;
+            c11 = fmin(fmin(z2, Ep), xmax) > fmax(kMe2 / Ep, z1);
+        }
+    }
+    const unsigned m9 = __ballot_sync(0xffffffffu, c9), m10 = __ballot_sync(0xffffffffu, c10);
+    const unsigned m11 = __ballot_sync(0xffffffffu, c11), mp = __ballot_sync(0xffffffffu, cp);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out + 0, (unsigned long long)__popc(mp));
+        atomicAdd(out + 1, (unsigned long long)__popc(m9));
+        atomicAdd(out + 2, (unsigned long long)__popc(m10));
+        atomicAdd(out + 3, (unsigned long long)__popc(m11));
+    }
+}
+
 // dense copy of one system's planes (debug / parity checks)
 __global__ void unpack_kernels_kernel(const double* __restrict__ Kws, int64_t np, int64_t k_off, int ne, double* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -511,30 +556,28 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
         const double ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
         const double bs = lnF[c + 1] - ms * y1;
         const double Elo = E[c];
-        // integrand = exp((ms+1) y + bs) * sigma(e^y).  Where the exponential factor changes by more than e^0.5 over the
-        // cell (e.g. next to a floored spectrum value) integrate in v = exp(kap (y - y_big)) from the large end: exact
-        // for constant sigma at any steepness; otherwise plain Gauss-Legendre in y.
-        const double kap = ms + 1.0, z = kap * (hi - y0);
-        const bool steep = fabs(z) > 0.5;
-        const double h = 0.5 * (hi - y0), m = 0.5 * (hi + y0);
-        const double yb = (z > 0.0) ? hi : y0;
-        const double vlo = steep ? exp(-fabs(z)) : 0.0;
-        const double pref = steep ? 0.5 * (1.0 - vlo) / fabs(kap) * exp(fma(kap, yb, bs)) : 0.0;
-        const double ikap = 1.0 / kap;
-        for (int k = 0; k < nq; ++k) {
-            double y, fe;
-            if (steep) {
-                const double v = fma(0.5 * (1.0 - vlo), 1.0 + qx[k], vlo);
-                y  = fma(log(v), ikap, yb);
-                fe = qw[k] * pref;
-            } else {
-                y  = fma(h, qx[k], m);
-                fe = qw[k] * h * exp(fma(kap, y, bs));
-            }
-            const double Ev = exp(y);
+        const bool kink_cell = (Elo < kKink15 && kKink15 < E[c + 1]);   // reaction 15 is integrated separately there
+        // integrand = exp(kap y + bs) * sigma(e^y), kap = ms + 1.  Next to a floored spectrum value (e.g. F_gamma(E0) = 0
+        // for pure e+e- injection) kap reaches ~1e4 and the cell's weight sits within 1/|kap| of one end.  The cell is
+        // therefore cut, starting from its large end, into pieces over which the exponent changes by <= 2 (at most 40
+        // e-folds are kept: the rest is < e^-40 of the cell), each piece with the plain nq-point rule.  Ordinary cells
+        // (|kap| * width <= 2) are a single piece.
+        const double kap = ms + 1.0, width = hi - y0;
+        const double len = fmin(width, 40.0 / fmax(fabs(kap), 1e-300));
+        const int nsub = max(1, (int)ceil(0.5 * fabs(kap) * len));
+        const double piece = len / (double)nsub;
+        const double start = (kap > 0.0) ? hi - len : y0;      // pieces cover [start, start + len]
+        for (int q = 0; q < nsub; ++q) {
+            const double a = start + piece * (double)q;
+            const double h = 0.5 * piece, m = a + h;
+            for (int k = 0; k < nq; ++k) {
+                const double y  = fma(h, qx[k], m);
+                const double Ev = exp(y);
+                const double fe = qw[k] * h * exp(fma(kap, y, bs));
 #pragma unroll
-            for (int r = 0; r < ACRO_NR; ++r)
-                if (kEth[r] <= Elo) acc[r] = fma(fe, cross_section_mb(r + 1, Ev, y), acc[r]);
+                for (int r = 0; r < ACRO_NR; ++r)
+                    if (kEth[r] <= Elo && !(r == 14 && kink_cell)) acc[r] = fma(fe, cross_section_mb(r + 1, Ev, y), acc[r]);
+            }
         }
     }
     // (B) the threshold cell of each reaction: lane r integrates [log Eth_r, min(cell end, log Emax)] with
@@ -565,11 +608,37 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
             }
         }
     }
+    // (C) reaction 15 (Be7+a>He3+He4): its closing polynomial changes sign at E = kKink15, where the reference clamps the
+    //     cross-section to zero (nucl.py:327-335) -- a kink inside one grid cell.  Lane 17 integrates that cell only up
+    //     to the kink (the part above it is identically zero) so that no rule straddles it.
+    if (lane == ACRO_NR && E[0] < kKink15 && kKink15 < E[top]) {
+        int c = (int)((log(kKink15) - lnE[0]) * (double)(ne - 1) / (lnE[ne - 1] - lnE[0]));
+        c = max(0, min(c, ne - 2));
+        while (c > 0 && !(E[c] < kKink15)) --c;
+        while (c < ne - 2 && E[c + 1] < kKink15) ++c;
+        if (kEth[14] <= E[c]) {      // otherwise the threshold-cell rule (B) owns this cell
+            const double y0 = lnE[c], y1 = lnE[c + 1];
+            const double hi = fmin(fmin(y1, lnEmax), log(kKink15));
+            if (hi > y0) {
+                const double ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
+                const double bs = lnF[c + 1] - ms * y1;
+                const double* tx = c_glx + gl_offset(16);
+                const double* tw = c_glw + gl_offset(16);
+                const double h = 0.5 * (hi - y0), m = 0.5 * (hi + y0);
+                for (int k = 0; k < 16; ++k) {
+                    const double y  = fma(h, tx[k], m);
+                    const double Ev = exp(y);
+                    thr = fma(tw[k] * h * exp(fma(ms + 1.0, y, bs)), cross_section_mb(15, Ev, y), thr);
+                }
+            }
+        }
+    }
     const double rate_E0 = g[top];   // Gamma_gamma(E0, T): the grid's last point is E0 (cascade.py:745, nucl.py:436)
 #pragma unroll
     for (int r = 0; r < ACRO_NR; ++r) {
         double v = warp_sum(acc[r]);
         v += __shfl_sync(0xffffffffu, thr, r);
+        if (r == 14) v += __shfl_sync(0xffffffffu, thr, ACRO_NR);
         if (lane == 0) {
             double rate = S0[0] * cross_section(r + 1, E0) / rate_E0;
             if (Emax > kEth[r]) rate += kMbToIMeV2 * v;
@@ -889,6 +958,15 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
         case 96: kernels_kernel<96><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
         default: kernels_kernel<64><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
     }
+    lc.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_work(const acro_batch_t& b, const acro_params_t& p, unsigned long long* out, cudaStream_t st,
+                              LaunchCounters& lc) {
+    if (b.n_pairs_total == 0) return cudaSuccess;
+    const int64_t blocks = (b.n_pairs_total + 127) / 128;
+    count_work_kernel<<<(unsigned)blocks, 128, 0, st>>>(b, out, p);
     lc.launches++;
     return cudaGetLastError();
 }

@@ -176,6 +176,8 @@ __constant__ const double kEth[17] = {2.224573, 6.257248, 8.481821, 5.493485, 7.
                                       26.071100, 3.698892, 15.794685, 2.467032, 7.249962, 10.948850, 1.586627, 5.605794,
                                       9.304680};
 constexpr double kMbToIMeV2 = 2.56819e-6;
+// E at which the closing polynomial of reaction 15 (nucl.py:328) changes sign: Q15 + 3.8259903470277856
+constexpr double kKink15 = 5.412617347027785;
 
 // N Q^p1 (E-Q)^p2 / E^p3 above threshold (nucl.py:209-214); lnE = log(E) is supplied by the caller
 __device__ __forceinline__ double sig_generic(double E, double lnE, double Q, double N, double p1, double p2, double p3) {

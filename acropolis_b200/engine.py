@@ -209,7 +209,13 @@ class Engine(object):
 
     def chunks(self, points, budget=None):
         """Greedy split of the point list so that each chunk's workspace fits the budget."""
-        budget = params.workspace_bytes if budget is None else budget
+        if budget is None:
+            budget = params.workspace_bytes
+            if budget is None:      # default: 40% of the device memory that is free at first use, at most 64 GiB
+                if not hasattr(self, "_auto_budget"):
+                    free, _ = torch.cuda.mem_get_info(self.device)
+                    self._auto_budget = int(min(64 * 1024**3, 0.4 * free))
+                budget = self._auto_budget
         out, cur, acc = [], [], 0
         for i, p in enumerate(points):
             c = self.point_cost_bytes(len(p.E_grid), len(p.T))
@@ -228,18 +234,25 @@ class Engine(object):
         self._sync_params()
         res = {k: [] for k in want}
         pending = []
+        self.last_h2d_bytes = self.last_d2h_bytes = 0
         for idx in self.chunks(points, budget):
-            pending.append(self._run_chunk([points[i] for i in idx], stages, want))
+            ch = self.stage([points[i] for i in idx], want)
+            self.launch(ch, stages)
+            pending.append(self.fetch(ch, want))
             if len(pending) > 1:                      # keep one chunk in flight while the next is assembled
                 self._collect(pending.pop(0), res)
         for pnd in pending:
             self._collect(pnd, res)
         return {k: (np.concatenate(v) if v else np.zeros(0)) for k, v in res.items()}
 
-    def _run_chunk(self, pts, stages, want):
+    def stage(self, pts, want=("Yf", "status"), resident=False):
+        """Assemble a chunk on the host, copy it to the device (one pinned H2D) and allocate its outputs.  With
+        ``resident`` the chunk gets its own device buffers (it can be launched repeatedly, e.g. by the benchmark)."""
         a, cnt = self.assemble(pts)
         st = self.stream
-        ptrs, _ = self._arena_for_chunk().upload([a[k] for k in self._ORDER], st)
+        arena = _Arena(self.device) if resident else self._arena_for_chunk()
+        ptrs, nbytes = arena.upload([a[k] for k in self._ORDER], st)
+        self.last_h2d_bytes = getattr(self, "last_h2d_bytes", 0) + nbytes
         b = _lib.Batch()
         for k, v in cnt.items():
             setattr(b, k, v)
@@ -263,17 +276,36 @@ class Engine(object):
         o = _lib.Out()
         for k, t in outs.items():
             setattr(o, k, t.data_ptr())
-        rc = self.lib.acro_run_batch(self.h, C.byref(b), C.byref(o), self._ws.data_ptr(), self._ws.numel(), stages,
-                                     st.cuda_stream)
+        return dict(cnt=cnt, batch=b, out=o, outs=outs, keep=(a, arena))
+
+    def launch(self, ch, stages=_lib.STAGE_ALL):
+        """Enqueue the stages of a staged chunk on the engine's stream (asynchronous)."""
+        rc = self.lib.acro_run_batch(self.h, C.byref(ch["batch"]), C.byref(ch["out"]), self._ws.data_ptr(), self._ws.numel(),
+                                     stages, self.stream.cuda_stream)
         self._check(rc, "acro_run_batch")
+
+    def fetch(self, ch, want):
+        """Enqueue the D2H copies of the wanted outputs into pinned memory; returns a pending handle."""
         host = {}
-        with torch.cuda.stream(st):
+        with torch.cuda.stream(self.stream):
             for k in want:
-                host[k] = torch.empty(outs[k].shape, dtype=outs[k].dtype, pin_memory=True)
-                host[k].copy_(outs[k], non_blocking=True)
+                host[k] = torch.empty(ch["outs"][k].shape, dtype=ch["outs"][k].dtype, pin_memory=True)
+                host[k].copy_(ch["outs"][k], non_blocking=True)
+                self.last_d2h_bytes = getattr(self, "last_d2h_bytes", 0) + host[k].numel() * host[k].element_size()
             ev = torch.cuda.Event()
-            ev.record(st)
-        return dict(host=host, ev=ev, cnt=cnt, keep=(outs, b, o, a), batch=b)
+            ev.record(self.stream)
+        return dict(host=host, ev=ev, cnt=ch["cnt"], keep=ch, batch=ch["batch"])
+
+    def count_work(self, ch):
+        """(pairs, N_a9, N_a10, N_a11) of a staged chunk (SURVEY.md 8d work census)."""
+        out = (C.c_int64 * 4)()
+        self._check(self.lib.acro_count_work(self.h, C.byref(ch["batch"]), C.byref(out), self.stream.cuda_stream), "acro_count_work")
+        return [int(v) for v in out]
+
+    def stage_ms(self):
+        ms = (C.c_float * 4)()
+        self._check(self.lib.acro_last_stage_ms(self.h, C.byref(ms)), "acro_last_stage_ms")
+        return np.array(list(ms), dtype=np.float64)
 
     def _arena_for_chunk(self):
         # two arenas alternate so that chunk n+1 can be staged while chunk n is still being read by the GPU
@@ -299,7 +331,9 @@ class Engine(object):
         """Dense K[5,NE,NE] (planes gg, eg, ge-, ge+, ee) of `point` at temperature index `it` (parity checks)."""
         self._sync_params()
         sub = PointSpec(point.E0, point.E_grid, point.T[it:it + 1], point.S0[it:it + 1], point.t_at_tmax)
-        pnd = self._run_chunk([sub], _lib.STAGE_RATES | _lib.STAGE_KERNELS, ("G",))
+        ch = self.stage([sub], ("G",))
+        self.launch(ch, _lib.STAGE_RATES | _lib.STAGE_KERNELS)
+        pnd = self.fetch(ch, ("G",))
         ne = len(point.E_grid)
         K = torch.empty(5 * ne * ne, dtype=torch.float64, device=self.device)
         with torch.cuda.stream(self.stream):
@@ -358,8 +392,8 @@ class Engine(object):
         n = mpdi.shape[0]
         d_mp = torch.from_numpy(mpdi.reshape(-1)).to(dev)
         d_md = torch.from_numpy(np.ascontiguousarray(mdcy, dtype=np.float64).reshape(-1)).to(dev)
-        d_f = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(factor, (n,)), dtype=np.float64)).to(dev)
-        d_t = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(t_at_tmax, (n,)), dtype=np.float64)).to(dev)
+        d_f = torch.from_numpy(np.array(np.broadcast_to(factor, (n,)), dtype=np.float64)).to(dev)
+        d_t = torch.from_numpy(np.array(np.broadcast_to(t_at_tmax, (n,)), dtype=np.float64)).to(dev)
         Yf = torch.empty(n * 27, dtype=torch.float64, device=dev)
         ex = torch.empty(n * 81, dtype=torch.float64, device=dev) if want_expm else None
         status = torch.zeros(n, dtype=torch.int32, device=dev)

@@ -145,6 +145,15 @@ def run_models(models, devices=None, want_matp=False):
     return (Yf, matp) if want_matp else Yf
 
 
+def run_points(model, param_sets, devices=None):
+    """Rows ``[sorted params..., 9 mean, 9 high, 9 low]`` for an arbitrary list of parameter dicts of one model class
+    (or ``functools.partial``): the batched form of ``BufferedScanner._run_single`` (reference scans.py:110-124).
+    Builds the models, stages their grids and source arrays, runs the CUDA path and reads the abundances back."""
+    models = [model(**p) for p in param_sets]
+    Yf = run_models(models, devices=devices)
+    return np.array([[*[p[k] for k in sorted(p)], *Y.transpose().reshape(Y.size)] for p, Y in zip(param_sets, Yf)])
+
+
 class BufferedScanner(object):
 
     def __init__(self, model, **kwargs):

@@ -178,6 +178,11 @@ int acro_measure_fp64_peak(acro_handle_t* h, double* tflops);
  * ms[0]=rates, ms[1]=kernels, ms[2]=solve+pdi, ms[3]=matrix.  Synchronises on the recorded events.             */
 int acro_last_stage_ms(acro_handle_t* h, float ms[4]);
 
+/* Work census of a (device-resident) batch for the roofline's algorithmic-flop figure: out[0] = (system,i,j>=i) pairs,
+ * out[1..3] = pairs with a non-empty range for the e->gamma, e->e and gamma->e thermal integrals (the reference's own
+ * limit tests, cascade.py:416-427, 516-534, 572-592).  Synchronous.                                              */
+int acro_count_work(acro_handle_t* h, const acro_batch_t* batch, int64_t out[4], void* stream);
+
 /* Number of kernel launches issued through this handle since creation. */
 int64_t acro_launch_count(const acro_handle_t* h);
 
