@@ -6,12 +6,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libacropolis_b200.so")
+LIB_PATH = os.environ.get("ACROPOLIS_B200_LIB") or os.path.join(_HERE, "libacropolis_b200.so")   # env override: kernel A/B builds
 
 NX, NY, NR, NK = 3, 9, 17, 5
 STAGE_RATES, STAGE_KERNELS, STAGE_SOLVE, STAGE_MATRIX, STAGE_ALL = 1, 2, 4, 8, 15
 ST_NONFINITE, ST_T_OUTSIDE, ST_DIRECT_RATE, ST_E0_ABOVE_GEV = 1, 2, 4, 8
 SC_NONE, SC_SEPARABLE, SC_DENSE = 0, 1, 2
+KERNELS_FAST, KERNELS_PLAIN_GL = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -29,7 +30,7 @@ class Tables(C.Structure):
 class Params(C.Structure):
     _fields_ = [("quad_order", C.c_int32), ("pdi_cell_order", C.c_int32), ("Emin", C.c_double),
                 ("approx_zero", C.c_double), ("Ephb_T_max", C.c_double), ("E_EC_max", C.c_double),
-                ("use_db", C.c_int32), ("reserved", C.c_int32)]
+                ("use_db", C.c_int32), ("kernel_mode", C.c_int32)]
 
 
 class Batch(C.Structure):

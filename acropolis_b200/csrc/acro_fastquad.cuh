@@ -1,0 +1,180 @@
+// acro_fastquad.cuh -- the production evaluation of the three Planck-weighted kernel integrals (a9, a10, a11).
+//
+// Same integrals, same limits as the reference (cascade.py:406-435, 507-540, 562-598) and as the plain Gauss-Legendre
+// version in acro_kernels.cu (kernel_mode = ACRO_KERNELS_PLAIN_GL, kept as the in-library cross-check); what changes
+// is how they are evaluated:
+//
+//  * STEEP regime  x_a/T > e  and  (x_b - x_a)/T >= 45  (the lower limit sits on the Wien tail of the thermal photons):
+//    with s = (x - x_a)/T the integral is  T e^{-x_a/T}/pi^2 * int_0^inf e^{-s} g(s) ds,  g smooth on the scale x_a/T > e,
+//    so a 24-point Gauss-Laguerre rule is exact to < 1e-10 (tools/proto: 4e-11 worst) -- and needs NO exponential per
+//    node (e^{-s_k} are constants).  Nodes beyond x_b (weight < e^-45) are masked.
+//  * otherwise the Q-point Gauss-Legendre rule in log(eps_bar) as before, but with the integrands reduced
+//    algebraically (q = x_a/x for the photon kernel so that log q = log x_a - y; Gamma*q = A/B with A + B = E' for
+//    the electron kernel; one shared reciprocal for the pair-creation function), division-free reciprocals and a
+//    branch-free exp.  The range tests of F and G are dropped: inside the integration limits they are identities
+//    ("CHECKED to never happen", cascade.py:33-35,63-66); kernel_mode = PLAIN_GL keeps them.
+#pragma once
+#include "acro_physics.cuh"
+
+#ifndef ACRO_FQ_UNROLL
+#define ACRO_FQ_UNROLL 1
+#endif
+#define ACRO_PRAGMA(x) _Pragma(#x)
+#define ACRO_UNROLL(n) ACRO_PRAGMA(unroll n)
+
+namespace acro {
+
+__constant__ double c_lag_s[24];    // Gauss-Laguerre nodes, n = 24
+__constant__ double c_lag_w[24];    // weights (include e^{-s})
+__constant__ double c_lag_es[24];   // e^{-s_k}
+
+__constant__ double c_half_range = 8.0;           // log-range [e-folds] up to which Q/2 nodes are used (a9, a11 only)
+constexpr double kSteepX = 2.718281828459045;   // x_a/T above which the Laguerre form is used (u_a > 1)
+constexpr double kSteepSpan = 45.0;             // and the span (x_b - x_a)/T must exceed this
+
+// 1/x to full double precision: MUFU.RCP64H seed + two Newton steps, no special-case handling (x finite, normal, != 0)
+__device__ __forceinline__ double frcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// Polynomial coefficients live in constant memory so that every FMA takes its constant straight from the constant bank
+// (as 64-bit immediates they cost two register moves each inside the node loops: ~25 % of the issued instructions).
+__constant__ double c_exp[14] = {1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03,
+                                       1.3888888888888889e-03, 1.9841269841269841e-04, 2.4801587301587302e-05,
+                                       2.7557319223985888e-06, 2.7557319223985893e-07, 2.5052108385441720e-08,
+                                       2.0876756987868100e-09, 1.6059043836821613e-10};
+__constant__ double c_exp_rr[3] = {1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10};
+// log: log(m) = 2 atanh(f), f = (m-1)/(m+1), m in [sqrt(1/2), sqrt(2)): 2f (1 + f^2/3 + ... + f^18/19), |f| <= 0.1716
+__constant__ double c_log[10] = {2.0, 2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0,
+                                       2.0 / 17.0, 2.0 / 19.0};
+__constant__ double c_ln2[2] = {6.93147180369123816490e-01, 1.90821492927058770002e-10};
+__constant__ double c_bose[4] = {1.0 / 12.0, -1.0 / 720.0, 1.0 / 30240.0, -1.0 / 1209600.0};
+
+// exp(x) for -700 < x < 700 (degree-13 Taylor polynomial on [-ln2/2, ln2/2], remainder 4e-18), no range handling
+__device__ __forceinline__ double fexp(double x) {
+    const double t = fma(x, c_exp_rr[0], 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, c_exp_rr[1], x);
+    r = fma(kf, c_exp_rr[2], r);
+    double p = c_exp[13];
+#pragma unroll
+    for (int i = 12; i >= 0; --i) p = fma(p, r, c_exp[i]);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// log(x) for positive normal x (no special cases): exponent/mantissa split, atanh series, error ~2e-16 relative to |log|+1
+__device__ __forceinline__ double flog(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;          // mantissa in [1, 2)
+    if (hi >= 0x3ff6a09e) { hi -= 0x00100000; e += 1; }   // m >= sqrt(2): halve it
+    const double m = __hiloint2double(hi, lo);
+    const double f = (m - 1.0) * frcp(m + 1.0);
+    const double f2 = f * f;
+    double p = c_log[9];
+#pragma unroll
+    for (int i = 8; i >= 0; --i) p = fma(p, f2, c_log[i]);
+    const double ef = (double)e;
+    return fma(ef, c_ln2[0], fma(p, f, ef * c_ln2[1]));
+}
+
+// 1/(e^v - 1), v > 0
+__device__ __forceinline__ double bose_inv(double v) {
+    if (v < 0.125) {   // Laurent series: 1/v - 1/2 + v/12 - v^3/720 + v^5/30240 - v^7/1209600 (rel. error < 1e-15 here)
+        const double v2 = v * v;
+        double p = fma(v2, c_bose[3], c_bose[2]);
+        p = fma(p, v2, c_bose[1]);
+        p = fma(p, v2, c_bose[0]);
+        return fma(p, v, frcp(v) - 0.5);
+    }
+    const double e = fexp(-v);
+    return e * frcp(1.0 - e);
+}
+
+enum { KIND_IC_PHOTON = 0, KIND_IC_ELECTRON = 1, KIND_PC_ELECTRON = 2 };
+
+struct PairConst {   // per-(E,E') constants of the three integrands
+    double E, Ep, dE;
+    double c9;        // r^2/(2+2r), r = E/(E'-E)
+    double c10;       // me^2/(4 E')
+    double i2Ep;      // 1/(2 E')
+};
+
+// integrand WITHOUT the Bose factor and without the power of x that goes with it:
+//   IC kernels:  F(...)            (the measure supplies x^2 dlogx = x dx)
+//   pair kernel: G(...)            (the measure supplies x dlogx = dx)
+template <int KIND>
+__device__ __forceinline__ double integrand_core(const PairConst& c, double x, double x_a, double lnx_minus_lnxa /* log(x/x_a) */,
+                                                 bool have_log) {
+    if (KIND == KIND_IC_PHOTON) {
+        const double q = x_a * frcp(x);
+        const double lq = have_log ? -lnx_minus_lnxa : flog(q);
+        const double omq = 1.0 - q;
+        return fma(2.0 * q, lq, fma(fma(2.0, q, 1.0), omq, c.c9 * omq));
+    } else if (KIND == KIND_IC_ELECTRON) {
+        const double A = c.dE + x, B = c.E - x;
+        const double ixb = frcp(x * B);
+        const double q = c.c10 * A * ixb;
+        const double omq = 1.0 - q;
+        return fma(2.0 * q, flog(q), fma(fma(2.0, q, 1.0), omq, A * A * omq * c.i2Ep * (x * ixb)));
+    } else {
+        const double s = c.Ep + x, Eep = s - c.E, ee = c.E * Eep;
+        const double R = frcp(ee * s * x);
+        const double iee = R * s * x, is = R * ee * x, ix = R * ee * s;
+        const double s2 = s * s;
+        double sud = 4.0 * s2 * flog(4.0 * x * ee * is * (1.0 / kMe2)) * iee;
+        sud = fma(fma(kMe2 * ix, is, -1.0), (s2 * s2) * (iee * iee), sud);
+        sud = fma(2.0 * fma(2.0 * x, s, -kMe2), s2 * iee * (1.0 / kMe2), sud);
+        return fma(-8.0 * (1.0 / kMe2), x * s, sud);
+    }
+}
+
+// int_{x_a}^{x_b} core(x) * x^{P-1} / (pi^2 (e^{x/T}-1)) dx   with P = 2 (IC) or 1 (pair creation)
+template <int KIND, int Q>
+__device__ __forceinline__ double thermal_integral(const PairConst& c, double T, double x_a, double x_b) {
+    const double iT = 1.0 / T;
+    const double va = x_a * iT;
+    if (va > kSteepX && (x_b - x_a) * iT >= kSteepSpan) {
+        // Gauss-Laguerre in s = (x - x_a)/T
+        const double Ea = fexp(-va);
+        double sum = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < 24; ++k) {
+            const double x = fma(c_lag_s[k], T, x_a);
+            if (x < x_b) {
+                double g = integrand_core<KIND>(c, x, x_a, 0.0, false);
+                if (KIND != KIND_PC_ELECTRON) g *= x;
+                sum = fma(c_lag_w[k] * g, frcp(fma(-Ea, c_lag_es[k], 1.0)), sum);
+            }
+        }
+        return sum * T * Ea * (1.0 / kPi2);
+    }
+    const double a = flog(x_a), b = flog(x_b);
+    const double h = 0.5 * (b - a), m = 0.5 * (b + a);
+    // node count by the width of the log-range: the Q-point rule, or Q/2 points when the range is short.  Measured on a
+    // 168-point slice sample against Q=96: with ranges <= 8 e-folds at Q/2 = 32 the photon (a9) and pair (a11) kernels
+    // stay within 1e-9; the electron kernel (a10) does not (2e-7 already at 4.5 e-folds) and always uses Q.
+    const bool half = (Q >= 32) && (KIND != KIND_IC_ELECTRON) && (b - a <= c_half_range);
+    const int n = half ? Q / 2 : Q;
+    const double* gx = c_glx + (half ? gl_offset(Q / 2 < 8 ? 8 : Q / 2) : gl_offset(Q));
+    const double* gw = c_glw + (half ? gl_offset(Q / 2 < 8 ? 8 : Q / 2) : gl_offset(Q));
+    double sum = 0.0;
+    ACRO_UNROLL(ACRO_FQ_UNROLL)
+    for (int k = 0; k < n; ++k) {
+        const double y = fma(h, gx[k], m);
+        const double x = fexp(y);
+        double g = integrand_core<KIND>(c, x, x_a, y - a, true) * x;
+        if (KIND != KIND_PC_ELECTRON) g *= x;
+        sum = fma(gw[k] * g, bose_inv(x * iT), sum);
+    }
+    return sum * h * (1.0 / kPi2);
+}
+
+}  // namespace acro

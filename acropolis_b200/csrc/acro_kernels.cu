@@ -12,6 +12,7 @@
 // None of this is a dense contraction, so no tensor-core (tcgen05) path exists for it: the bound is the FP64 pipe
 // for the quadrature kernels and HBM for solve/matrix.
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <cmath>
 
@@ -29,6 +30,33 @@ __constant__ double c_glw[kGLTotal];
 
 __host__ __device__ constexpr int gl_offset(int order) {
     return order == 8 ? 0 : order == 16 ? 8 : order == 32 ? 24 : order == 64 ? 56 : order == 96 ? 120 : 216;
+}
+
+}  // namespace acro
+#include "acro_fastquad.cuh"
+namespace acro {
+
+static void gauss_laguerre(int n, double* x, double* w) {   // alpha = 0; Newton on L_n with the classic initial guesses
+    std::vector<long double> xs(n);
+    for (int i = 0; i < n; ++i) {
+        long double z;
+        if (i == 0) z = 3.0L / (1.0L + 2.4L * n);
+        else if (i == 1) z = xs[0] + 15.0L / (1.0L + 2.5L * n);
+        else { const long double ai = i - 1; z = xs[i - 1] + ((1.0L + 2.55L * ai) / (1.9L * ai)) * (xs[i - 1] - xs[i - 2]); }
+        long double pp = 0, p2 = 0;
+        for (int it = 0; it < 100; ++it) {
+            long double p1 = 1, pm = 0;
+            for (int j = 1; j <= n; ++j) { const long double p3 = pm; pm = p1; p1 = ((2 * j - 1 - z) * pm - (j - 1) * p3) / j; }
+            p2 = pm;
+            pp = n * (p1 - p2) / z;
+            const long double z1 = z;
+            z = z1 - p1 / pp;
+            if (fabsl(z - z1) <= 1e-18L * fabsl(z)) break;
+        }
+        xs[i] = z;
+        x[i] = (double)z;
+        w[i] = (double)(-1.0L / (pp * n * p2));
+    }
 }
 
 static void gauss_legendre(int n, double* x, double* w) {
@@ -58,7 +86,14 @@ cudaError_t upload_quadrature_tables() {
     for (int o : orders) gauss_legendre(o, x.data() + gl_offset(o), w.data() + gl_offset(o));
     cudaError_t e = cudaMemcpyToSymbol(c_glx, x.data(), sizeof(double) * kGLTotal);
     if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_glw, w.data(), sizeof(double) * kGLTotal);
+    e = cudaMemcpyToSymbol(c_glw, w.data(), sizeof(double) * kGLTotal);
+    if (e != cudaSuccess) return e;
+    double ls[24], lw[24], les[24];
+    gauss_laguerre(24, ls, lw);
+    for (int i = 0; i < 24; ++i) les[i] = std::exp(-ls[i]);
+    if ((e = cudaMemcpyToSymbol(c_lag_s, ls, sizeof(ls))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_lag_w, lw, sizeof(lw))) != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_lag_es, les, sizeof(les));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -327,8 +362,61 @@ __device__ __forceinline__ KernelEntry eval_kernels(double E, double Ep, double 
     return k;
 }
 
+// Production version: same limits and closed forms, thermal integrals through acro_fastquad.cuh
 template <int Q>
-__global__ void __launch_bounds__(128) kernels_kernel(acro_batch_t b, double* __restrict__ Kws, DeviceTables t, acro_params_t p) {
+__device__ __forceinline__ KernelEntry eval_kernels_fast(double E, double Ep, double T, const Densities d, double Ephb_T_max) {
+    KernelEntry k;
+    const double xmax = Ephb_T_max * T;
+    PairConst c;
+    c.E = E; c.Ep = Ep; c.dE = Ep - E;
+    k.gg = kernel_photon_photon(E, Ep, T) + kernel_compton_core(E, Ep, d.ne);
+    k.eg = 0.0;
+    k.ee = 0.0;
+    const double pre_ic = 2.0 * kPi * (kAlpha * kAlpha) / (Ep * Ep);
+    const double ub = Ep - kMe2 / (4.0 * Ep);
+    const bool above = !(Ep < E + kMe);
+    if (above) {
+        const double llim = 0.25 * kMe2 * E / (Ep * Ep - Ep * E);
+        const double ulim = fmin(fmin(E, ub), xmax);
+        if (ulim > llim) {
+            const double r = E / c.dE;
+            c.c9 = r * r / (2.0 + 2.0 * r);
+            k.eg = pre_ic * thermal_integral<KIND_IC_PHOTON, Q>(c, T, llim, ulim);
+        }
+    }
+    if (E != Ep) {
+        const double pf = 0.25 * kMe2 / Ep - E;
+        const double qf = 0.25 * kMe2 * c.dE / Ep;
+        const double sq = sqrt((0.5 * pf) * (0.5 * pf) - qf);
+        const double z1 = -0.5 * pf - sq, z2 = -0.5 * pf + sq;
+        const double ulim = fmin(fmin(z2, ub), xmax);
+        if (ulim > z1) {
+            c.c10 = 0.25 * kMe2 / Ep;
+            c.i2Ep = 0.5 / Ep;
+            k.ee = pre_ic * thermal_integral<KIND_IC_ELECTRON, Q>(c, T, z1, ulim);
+        }
+    }
+    double pair = 0.0;
+    if (above) pair = d.nNZ2 * bh_dsdE_Z2(E, Ep);
+    if (!(Ep < kMe2 / (50.0 * T))) {
+        const double rt = sqrt(E * E - kMe2), den = 4.0 * Ep * c.dE + kMe2;
+        const double z1 = Ep * (kMe2 - 2.0 * c.dE * (rt - E)) / den;
+        const double z2 = Ep * (kMe2 + 2.0 * c.dE * (rt + E)) / den;
+        const double llim = fmax(kMe2 / Ep, z1);
+        const double ulim = fmin(fmin(z2, Ep), xmax);
+        if (ulim > llim)
+            pair += 0.25 * kPi * (kAlpha * kAlpha) * kMe2 * thermal_integral<KIND_PC_ELECTRON, Q>(c, T, llim, ulim) / (Ep * Ep * Ep);
+    }
+    k.gep = pair;
+    k.gem = pair + kernel_compton_core(Ep + kMe - E, Ep, d.ne);
+    return k;
+}
+
+#ifndef ACRO_KK_MINBLOCKS
+#define ACRO_KK_MINBLOCKS 6
+#endif
+template <int Q, bool FAST>
+__global__ void __launch_bounds__(128, ACRO_KK_MINBLOCKS) kernels_kernel(acro_batch_t b, double* __restrict__ Kws, DeviceTables t, acro_params_t p) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= b.n_pairs_total) return;
     const int s  = owner_of(b.sys_k_off, b.n_systems, tid);
@@ -346,7 +434,7 @@ __global__ void __launch_bounds__(128) kernels_kernel(acro_batch_t b, double* __
     const double* eg = b.e_grid + b.pt_e_off[pt];
     const double E = eg[i], Ep = eg[j], T = b.sys_T[s];
     const Densities d = densities(T, t.eta, t.Yp, t.YHe4);
-    const KernelEntry k = eval_kernels<Q>(E, Ep, T, d, p.Ephb_T_max);
+    const KernelEntry k = FAST ? eval_kernels_fast<Q>(E, Ep, T, d, p.Ephb_T_max) : eval_kernels<Q>(E, Ep, T, d, p.Ephb_T_max);
     const int64_t np = b.n_pairs_total;
     Kws[tid]          = k.gg;
     Kws[np + tid]     = k.eg;
@@ -948,15 +1036,32 @@ cudaError_t launch_direct_rates(const DeviceTables& t, const acro_params_t& p, d
     return cudaGetLastError();
 }
 
+cudaError_t set_half_range(double v) { return cudaMemcpyToSymbol(c_half_range, &v, sizeof(double)); }
+
 cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const acro_params_t& p, double* Kws,
                            cudaStream_t st, LaunchCounters& lc) {
     if (b.n_pairs_total == 0) return cudaSuccess;
+    if (const char* hr = getenv("ACRO_HALF_RANGE")) {   // experiment knob (A/B runs only)
+        static double last = -1.0;
+        const double v = atof(hr);
+        if (v != last) { cudaMemcpyToSymbolAsync(c_half_range, &v, sizeof(double), 0, cudaMemcpyHostToDevice, st); last = v; }
+    }
     const int64_t blocks = (b.n_pairs_total + 127) / 128;
-    switch (p.quad_order) {
-        case 16: kernels_kernel<16><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
-        case 32: kernels_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
-        case 96: kernels_kernel<96><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
-        default: kernels_kernel<64><<<(unsigned)blocks, 128, 0, st>>>(b, Kws, t, p); break;
+    const unsigned g = (unsigned)blocks;
+    if (p.kernel_mode == ACRO_KERNELS_PLAIN_GL) {
+        switch (p.quad_order) {
+            case 16: kernels_kernel<16, false><<<g, 128, 0, st>>>(b, Kws, t, p); break;
+            case 32: kernels_kernel<32, false><<<g, 128, 0, st>>>(b, Kws, t, p); break;
+            case 96: kernels_kernel<96, false><<<g, 128, 0, st>>>(b, Kws, t, p); break;
+            default: kernels_kernel<64, false><<<g, 128, 0, st>>>(b, Kws, t, p); break;
+        }
+    } else {
+        switch (p.quad_order) {
+            case 16: kernels_kernel<16, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;
+            case 32: kernels_kernel<32, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;
+            case 96: kernels_kernel<96, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;
+            default: kernels_kernel<64, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;
+        }
     }
     lc.launches++;
     return cudaGetLastError();

@@ -136,9 +136,9 @@ class Engine(object):
 
     def _sync_params(self):
         key = (params.quad_order, params.pdi_cell_order, params.Emin, params.approx_zero, params.Ephb_T_max,
-               params.E_EC_max, bool(flags.usedb and self._use_db))
+               params.E_EC_max, bool(flags.usedb and self._use_db), int(params.kernel_mode))
         if key != self._params_key:
-            p = _lib.Params(*key[:6], int(key[6]), 0)
+            p = _lib.Params(*key[:6], int(key[6]), key[7])
             self._check(self.lib.acro_set_params(self.h, C.byref(p)), "acro_set_params")
             self._params_key = key
 

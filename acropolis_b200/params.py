@@ -41,4 +41,5 @@ NT_pd = 20             # temperature-grid points per decade
 # B200-path parameters (no reference counterpart)
 quad_order = 64        # Gauss-Legendre nodes per thermal kernel integral (16, 32, 64, 96)
 pdi_cell_order = 8     # GL nodes per energy-grid cell of the pdi-rate integrals (8, 16)
+kernel_mode = 0        # 0: fast evaluation of the thermal kernel integrals (default); 1: plain Gauss-Legendre cross-check
 workspace_bytes = None  # HBM budget [bytes] for the kernel planes of one chunk of points; None = 40% of free HBM (<= 64 GiB)

@@ -53,6 +53,10 @@ extern "C" {
 #define ACRO_ST_DIRECT_RATE   4  /* at least one rate came from the direct 2-D integral (outside rates.db)   */
 #define ACRO_ST_E0_ABOVE_GEV  8  /* injection energy > 1 GeV ("results cannot be trusted")                   */
 
+/* how the three thermal kernel integrals are evaluated (same integrals and limits either way) */
+#define ACRO_KERNELS_FAST      0  /* Gauss-Laguerre on the Wien tail, reduced integrands, division-free (default) */
+#define ACRO_KERNELS_PLAIN_GL  1  /* plain Q-point Gauss-Legendre in log(eps_bar) with the reference's F/G incl. range tests */
+
 /* continuous-source representation */
 #define ACRO_SC_NONE       0  /* SC == 0 for all species (models.py:197-206 defaults)                        */
 #define ACRO_SC_SEPARABLE  1  /* SC[X](E_i,T_s) = sc[s*3+X] * sc_E[(pt_e_off+i)*3+X]   (FSR form, models.py:276-287) */
@@ -81,7 +85,7 @@ typedef struct {
     double  Ephb_T_max;      /* 200                                                                               */
     double  E_EC_max;        /* 10                                                                                */
     int32_t use_db;          /* flags.usedb                                                                       */
-    int32_t reserved;
+    int32_t kernel_mode;     /* ACRO_KERNELS_FAST (default) or ACRO_KERNELS_PLAIN_GL                              */
 } acro_params_t;
 
 /*

@@ -31,8 +31,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.acro_abi_version() == 1
     p = _lib.Params()
     lib.acro_default_params(p)
-    assert (p.quad_order, p.pdi_cell_order, p.Emin, p.approx_zero, p.Ephb_T_max, p.E_EC_max, p.use_db) == \
-        (64, 8, 1.5, 1e-200, 200.0, 10.0, 1)
+    assert (p.quad_order, p.pdi_cell_order, p.Emin, p.approx_zero, p.Ephb_T_max, p.E_EC_max, p.use_db, p.kernel_mode) == \
+        (64, 8, 1.5, 1e-200, 200.0, 10.0, 1, 0)
 
 
 def test_library_is_built_for_sm_100a():
