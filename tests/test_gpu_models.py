@@ -36,6 +36,14 @@ def test_annihilation_model_cfg2(gpu_engine):
     assert relerr(Yf[[1, 2, 4, 5, 7]], z["Yf"][[1, 2, 4, 5, 7]], 1e-30) < 1e-4
 
 
+def test_resonance_model(gpu_engine):
+    """BASELINE config 4 point: BenchmarkModel3(mchi=10, delta=1e-2, gammad=1e-3, gammav=1e-12) (52 s in the reference)."""
+    from acropolis_b200.ext.benchmarks import BenchmarkModel3
+    z = golden("resonance_b3.npz")
+    Yf = BenchmarkModel3(mchi=10., delta=1e-2, gammad=1e-3, gammav=1e-12).run_disintegration()
+    assert relerr(Yf, z["Yf"], 1e-30) < 5e-4 and relerr(Yf[[1, 2, 4, 5]], z["Yf"][[1, 2, 4, 5]], 1e-30) < 1e-4
+
+
 def test_trivial_model_below_threshold(gpu_engine):
     from acropolis_b200.models import DecayModel
     m = DecayModel(2.0, 1e5, 10., 1e-10, 0., 1.)      # E0 = 1 MeV <= Emin (models.py:65-71)

@@ -226,3 +226,28 @@ def test_fsr_shape_matches_scalar_hook():
     ref = np.array([m._source_photon_c(e, T) for e in E])
     assert np.allclose(_fsr_shape(E, 15.0) * m._source_electron_0(T), ref, rtol=1e-14, atol=0)
     assert ref[-1] == 0.0
+
+
+def test_resonance_model_hooks_match_reference():
+    """ResonanceModel (ext/models.py:139-325): T_kd from estimate_tempkd_ee, the Breit-Wigner thermal average and the
+    resulting source arrays, fixed-order vectorised quadrature vs the reference's adaptive quad calls."""
+    from acropolis_b200.ext.benchmarks import BenchmarkModel1, BenchmarkModel2, BenchmarkModel3
+    kw = dict(mchi=10., delta=1e-2, gammad=1e-3, gammav=1e-12)
+    z, z12 = golden("resonance_b3.npz"), golden("resonance_b12_hooks.npz")
+    m3 = BenchmarkModel3(**kw)
+    assert m3._sTkd == pytest.approx(float(z["tempkd"]), rel=1e-7)
+    assert np.allclose(m3._sigma_v_array(z["sigma_v_T"]), z["sigma_v"], rtol=1e-6, atol=0)
+    assert m3._sigma_v(float(z["sigma_v_T"][3])) == pytest.approx(float(z["sigma_v"][3]), rel=1e-6)
+    sp = m3.point_spec()
+    assert np.array_equal(sp.E_grid, z["E_grid"]) and np.array_equal(sp.T, z["T"])
+    assert relerr(sp.S0, z["S0"], 1e-300) < 1e-5          # the reference's own quad noise (eps=1e-3) is ~5e-7 here
+    SC = sp.sc[:, :, None] * sp.sc_E.T[None, :, :]
+    assert relerr(SC, z["SC"], 1e-300) < 1e-5
+    for tag, M in (("b1", BenchmarkModel1), ("b2", BenchmarkModel2)):
+        m = M(**kw)
+        assert m._sTkd == pytest.approx(float(z12[tag + "_tempkd"]), rel=1e-7)
+        assert np.allclose(m._sigma_v_array(z12[tag + "_sigma_v_T"]), z12[tag + "_sigma_v"], rtol=1e-6, atol=0)
+    from acropolis_b200.pprint import AcropolisError
+    from acropolis_b200.ext.models import ResonanceModel
+    with pytest.raises(AcropolisError):
+        ResonanceModel(10., 2.0, 1e-3, 1e-12, 1, 1e-3)     # delta > 1
