@@ -56,7 +56,7 @@ static int check_params(acro_handle* h, const acro_params_t* p) {
     if (!(p->quad_order == 16 || p->quad_order == 32 || p->quad_order == 64 || p->quad_order == 96))
         return fail(h, ACRO_EINVAL, "quad_order must be 16, 32, 64 or 96");
     if (!(p->pdi_cell_order == 8 || p->pdi_cell_order == 16)) return fail(h, ACRO_EINVAL, "pdi_cell_order must be 8 or 16");
-    if (!(p->kernel_mode == ACRO_KERNELS_FAST || p->kernel_mode == ACRO_KERNELS_PLAIN_GL)) return fail(h, ACRO_EINVAL, "bad kernel_mode");
+    if (!(p->kernel_mode == ACRO_KERNELS_FAST || p->kernel_mode == ACRO_KERNELS_PLAIN_GL || p->kernel_mode == ACRO_KERNELS_PER_T)) return fail(h, ACRO_EINVAL, "bad kernel_mode");
     if (!(p->Emin > 0 && p->approx_zero > 0 && p->Ephb_T_max > 0 && p->E_EC_max > 0)) return fail(h, ACRO_EINVAL, "bad params");
     return ACRO_OK;
 }

@@ -30,7 +30,7 @@ __constant__ double c_lag_es[24];   // e^{-s_k}
 
 __constant__ double c_half_range = 8.0;           // log-range [e-folds] up to which Q/2 nodes are used (a9, a11 only)
 constexpr double kSteepX = 2.718281828459045;   // x_a/T above which the Laguerre form is used (u_a > 1)
-constexpr double kSteepSpan = 45.0;             // and the span (x_b - x_a)/T must exceed this
+constexpr double kSteepSpan = 32.0;             // and the span (x_b - x_a)/T must exceed this (truncation e^-32)
 
 // 1/x to full double precision: MUFU.RCP64H seed + two Newton steps, no special-case handling (x finite, normal, != 0)
 __device__ __forceinline__ double frcp(double x) {
@@ -155,6 +155,24 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
             }
         }
         return sum * T * Ea * (1.0 / kPi2);
+    }
+    if (va > kSteepX) {
+        // Wien tail with a short span S = (x_b - x_a)/T < 32: Gauss-Legendre (32 nodes) in s on [0, S] with the explicit
+        // weight e^{-s}; no logarithmic variable needed because the integrand varies on the scale x_a/T > e.
+        const double S = (x_b - x_a) * iT;
+        const double Ea = fexp(-va);
+        const double hs = 0.5 * S;
+        double sum = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < 32; ++k) {
+            const double sk = fma(hs, c_glx[gl_offset(32) + k], hs);
+            const double x = fma(sk, T, x_a);
+            const double es = fexp(-sk);
+            double g = integrand_core<KIND>(c, x, x_a, 0.0, false);
+            if (KIND != KIND_PC_ELECTRON) g *= x;
+            sum = fma(c_glw[gl_offset(32) + k] * g * es, frcp(fma(-Ea, es, 1.0)), sum);
+        }
+        return sum * hs * T * Ea * (1.0 / kPi2);
     }
     const double a = flog(x_a), b = flog(x_b);
     const double h = 0.5 * (b - a), m = 0.5 * (b + a);

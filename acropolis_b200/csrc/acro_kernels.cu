@@ -34,6 +34,7 @@ __host__ __device__ constexpr int gl_offset(int order) {
 
 }  // namespace acro
 #include "acro_fastquad.cuh"
+#include "acro_tshared.cuh"
 namespace acro {
 
 static void gauss_laguerre(int n, double* x, double* w) {   // alpha = 0; Newton on L_n with the classic initial guesses
@@ -93,7 +94,23 @@ cudaError_t upload_quadrature_tables() {
     for (int i = 0; i < 24; ++i) les[i] = std::exp(-ls[i]);
     if ((e = cudaMemcpyToSymbol(c_lag_s, ls, sizeof(ls))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_lag_w, lw, sizeof(lw))) != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_lag_es, les, sizeof(les));
+    if ((e = cudaMemcpyToSymbol(c_lag_es, les, sizeof(les))) != cudaSuccess) return e;
+    // Legendre tables of the 16-node panels (acro_tshared.cuh)
+    double modal[kPanN][kPanN], rec[kPanN][2];
+    const double* gx = x.data() + gl_offset(kPanN);
+    const double* gw = w.data() + gl_offset(kPanN);
+    for (int m = 0; m < kPanN; ++m) {
+        long double pm = 1, pc = gx[m];
+        for (int j = 0; j < kPanN; ++j) {
+            const long double pj = (j == 0) ? 1.0L : (j == 1 ? (long double)gx[m] : 0.0L);
+            long double val = pj;
+            if (j >= 2) { val = ((2 * j - 1) * (long double)gx[m] * pc - (j - 1) * pm) / j; pm = pc; pc = val; }
+            modal[j][m] = (double)((2 * j + 1) / 2.0L * gw[m] * val);
+        }
+    }
+    for (int j = 0; j < kPanN; ++j) { rec[j][0] = (2.0 * j + 1.0) / (j + 1.0); rec[j][1] = (double)j / (j + 1.0); }
+    if ((e = cudaMemcpyToSymbol(c_leg_modal, modal, sizeof(modal))) != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_leg_rec, rec, sizeof(rec));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -122,9 +139,6 @@ __device__ __forceinline__ int owner_of(const int64_t* __restrict__ off, int n, 
     return lo;
 }
 
-__host__ __device__ __forceinline__ int64_t tri_row_off(int i, int ne) {   // first entry of row i in packed upper-tri
-    return (int64_t)i * ne - ((int64_t)i * (i - 1)) / 2;
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // (i.a)+(v)  total rates G[3,NE] per system
@@ -362,9 +376,16 @@ __device__ __forceinline__ KernelEntry eval_kernels(double E, double Ep, double 
     return k;
 }
 
-// Production version: same limits and closed forms, thermal integrals through acro_fastquad.cuh
+// Production version: same limits and closed forms; thermal integrals either picked up from the temperature-shared
+// producer kernel (acro_tshared.cuh) or evaluated here (Gauss-Laguerre / Gauss-Legendre, acro_fastquad.cuh).
+struct SharedInfo {
+    bool on;            // producer results are present in the K planes
+    double x_bot, Tmin; // bottom of the point's shared grid, lowest temperature of the point
+};
+
 template <int Q>
-__device__ __forceinline__ KernelEntry eval_kernels_fast(double E, double Ep, double T, const Densities d, double Ephb_T_max) {
+__device__ __forceinline__ KernelEntry eval_kernels_fast(double E, double Ep, double T, const Densities d, double Ephb_T_max,
+                                                         const SharedInfo si, const double* __restrict__ raw, int64_t np) {
     KernelEntry k;
     const double xmax = Ephb_T_max * T;
     PairConst c;
@@ -373,39 +394,43 @@ __device__ __forceinline__ KernelEntry eval_kernels_fast(double E, double Ep, do
     k.eg = 0.0;
     k.ee = 0.0;
     const double pre_ic = 2.0 * kPi * (kAlpha * kAlpha) / (Ep * Ep);
-    const double ub = Ep - kMe2 / (4.0 * Ep);
-    const bool above = !(Ep < E + kMe);
-    if (above) {
-        const double llim = 0.25 * kMe2 * E / (Ep * Ep - Ep * E);
-        const double ulim = fmin(fmin(E, ub), xmax);
-        if (ulim > llim) {
-            const double r = E / c.dE;
-            c.c9 = r * r / (2.0 + 2.0 * r);
-            k.eg = pre_ic * thermal_integral<KIND_IC_PHOTON, Q>(c, T, llim, ulim);
+    const PairLimits L = pair_limits(E, Ep);
+    if (L.xa9 > 0.0) {
+        const double ulim = fmin(L.xb9, xmax);
+        if (ulim > L.xa9) {
+            double I;
+            if (si.on && shared_regime(L.xa9, L.xb9, T, Ephb_T_max, si.x_bot, si.Tmin)) I = raw[1 * np];
+            else {
+                const double r = E / c.dE;
+                c.c9 = r * r / (2.0 + 2.0 * r);
+                I = thermal_integral<KIND_IC_PHOTON, Q>(c, T, L.xa9, ulim);
+            }
+            k.eg = pre_ic * I;
         }
     }
-    if (E != Ep) {
-        const double pf = 0.25 * kMe2 / Ep - E;
-        const double qf = 0.25 * kMe2 * c.dE / Ep;
-        const double sq = sqrt((0.5 * pf) * (0.5 * pf) - qf);
-        const double z1 = -0.5 * pf - sq, z2 = -0.5 * pf + sq;
-        const double ulim = fmin(fmin(z2, ub), xmax);
-        if (ulim > z1) {
-            c.c10 = 0.25 * kMe2 / Ep;
-            c.i2Ep = 0.5 / Ep;
-            k.ee = pre_ic * thermal_integral<KIND_IC_ELECTRON, Q>(c, T, z1, ulim);
+    if (L.xa10 > 0.0) {
+        const double ulim = fmin(L.xb10, xmax);
+        if (ulim > L.xa10) {
+            double I;
+            if (si.on && shared_regime(L.xa10, L.xb10, T, Ephb_T_max, si.x_bot, si.Tmin)) I = raw[4 * np];
+            else {
+                c.c10 = 0.25 * kMe2 / Ep;
+                c.i2Ep = 0.5 / Ep;
+                I = thermal_integral<KIND_IC_ELECTRON, Q>(c, T, L.xa10, ulim);
+            }
+            k.ee = pre_ic * I;
         }
     }
     double pair = 0.0;
-    if (above) pair = d.nNZ2 * bh_dsdE_Z2(E, Ep);
+    if (L.xa9 > 0.0) pair = d.nNZ2 * bh_dsdE_Z2(E, Ep);     // same condition E' >= E + me (cascade.py:554)
     if (!(Ep < kMe2 / (50.0 * T))) {
-        const double rt = sqrt(E * E - kMe2), den = 4.0 * Ep * c.dE + kMe2;
-        const double z1 = Ep * (kMe2 - 2.0 * c.dE * (rt - E)) / den;
-        const double z2 = Ep * (kMe2 + 2.0 * c.dE * (rt + E)) / den;
-        const double llim = fmax(kMe2 / Ep, z1);
-        const double ulim = fmin(fmin(z2, Ep), xmax);
-        if (ulim > llim)
-            pair += 0.25 * kPi * (kAlpha * kAlpha) * kMe2 * thermal_integral<KIND_PC_ELECTRON, Q>(c, T, llim, ulim) / (Ep * Ep * Ep);
+        const double ulim = fmin(L.xb11, xmax);
+        if (ulim > L.xa11) {
+            double I;
+            if (si.on && shared_regime(L.xa11, L.xb11, T, Ephb_T_max, si.x_bot, si.Tmin)) I = raw[3 * np];
+            else I = thermal_integral<KIND_PC_ELECTRON, Q>(c, T, L.xa11, ulim);
+            pair += 0.25 * kPi * (kAlpha * kAlpha) * kMe2 * I / (Ep * Ep * Ep);
+        }
     }
     k.gep = pair;
     k.gem = pair + kernel_compton_core(Ep + kMe - E, Ep, d.ne);
@@ -434,8 +459,19 @@ __global__ void __launch_bounds__(128, ACRO_KK_MINBLOCKS) kernels_kernel(acro_ba
     const double* eg = b.e_grid + b.pt_e_off[pt];
     const double E = eg[i], Ep = eg[j], T = b.sys_T[s];
     const Densities d = densities(T, t.eta, t.Yp, t.YHe4);
-    const KernelEntry k = FAST ? eval_kernels_fast<Q>(E, Ep, T, d, p.Ephb_T_max) : eval_kernels<Q>(E, Ep, T, d, p.Ephb_T_max);
     const int64_t np = b.n_pairs_total;
+    KernelEntry k;
+    if (FAST) {
+        SharedInfo si;
+        si.on = (p.kernel_mode == ACRO_KERNELS_FAST);
+        const int s_first = b.pt_sys_off[pt], nt = b.pt_nt[pt];
+        si.Tmin = b.sys_T[s_first];
+        const SharedGrid g = shared_grid(si.Tmin, b.sys_T[s_first + nt - 1], eg[ne - 1], p.Ephb_T_max);
+        si.x_bot = exp(g.y_bot);
+        k = eval_kernels_fast<Q>(E, Ep, T, d, p.Ephb_T_max, si, Kws + tid, np);
+    } else {
+        k = eval_kernels<Q>(E, Ep, T, d, p.Ephb_T_max);
+    }
     Kws[tid]          = k.gg;
     Kws[np + tid]     = k.eg;
     Kws[2 * np + tid] = k.gem;
@@ -1056,6 +1092,21 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
             default: kernels_kernel<64, false><<<g, 128, 0, st>>>(b, Kws, t, p); break;
         }
     } else {
+        if (p.kernel_mode == ACRO_KERNELS_FAST) {   // temperature-shared producer (acro_tshared.cuh)
+            const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT);
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaError_t e = cudaFuncSetAttribute(kernels_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                attr_set = true;
+            }
+            const int64_t tri_max = (int64_t)b.ne_max * (b.ne_max + 1) / 2;
+            dim3 grid((unsigned)((tri_max + kSharedThreads - 1) / kSharedThreads), (unsigned)b.n_points);
+            kernels_shared_kernel<<<grid, kSharedThreads, smem, st>>>(b, Kws, p);
+            lc.launches++;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
         switch (p.quad_order) {
             case 16: kernels_kernel<16, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;
             case 32: kernels_kernel<32, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;

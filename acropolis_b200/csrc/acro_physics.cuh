@@ -22,6 +22,11 @@ constexpr double kHbar  = 6.582119514e-22;
 constexpr double kTauN  = 8.794e2;
 constexpr double kTauT  = 5.605e8;
 
+// first entry of row i in a packed upper-triangular NE x NE plane (row-major, j >= i)
+__host__ __device__ __forceinline__ long long tri_row_off(int i, int ne) {
+    return (long long)i * ne - ((long long)i * (i - 1)) / 2;
+}
+
 struct Densities {
     double ne;     // electron density          (cascade.py:264-266)
     double nNZ2;   // sum_N Z^2 n_N             (cascade.py:269-271)

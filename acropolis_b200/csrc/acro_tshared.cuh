@@ -1,0 +1,327 @@
+// acro_tshared.cuh -- temperature-shared evaluation of the three thermal kernel integrals.
+//
+// In   K(E,E',T) ~ int f(E,E',x) * x^p / (e^{x/T} - 1) dlog x   the factor f (the functions F, G of cascade.py:29-80) does
+// not depend on T and the Bose factor does not depend on (E,E').  For all temperatures of one model point whose lower
+// limit is not on the Wien tail (x_a <= e T) and whose upper limit is the thermal cut-off (200 T < x_b0), the integral is
+// therefore evaluated on ONE panel grid in y = log x that is shared by every pair and every temperature of the point:
+//
+//   * panels of 16 Gauss-Legendre nodes: width 1 e-fold from y_top = log(min(200 Tmax, E0)) down to log(Tmin) - 1 (where
+//     some temperature still sees the Planck roll-off), width 2 below, down to log(Tmin) - 25 (what lies below
+//     contributes < 2e-11);
+//   * per temperature tile, the Bose factors at the grid nodes (and their Legendre coefficients per panel) are staged in
+//     SHARED MEMORY once per thread block -- the "thermal-photon grid" of BASELINE.json:north_star;
+//   * each thread owns one (E,E') pair: f is evaluated once per node and accumulated into TT temperature sums with one
+//     FMA each; the panel that contains the lower limit is integrated on its own nodes against the Legendre expansion of
+//     the Bose factor (exact for what the panel rule itself resolves), and so is the panel that contains the upper limit
+//     when that is the kinematic one (x_b0 < 200 T); the thermal cut-off 200 T is applied as zeros in the Bose table.
+//
+// Measured against the converged per-(pair,T) rule (tools/proto/tshared_proto.py): <= 1e-11 for x_a <= e T.
+// The raw integrals are written into the K planes (eg, ee, ge+ slots); kernels_kernel<.,FAST> then picks them up for the
+// (pair,T) combinations that satisfy shared_regime() and evaluates the rest itself (Gauss-Laguerre / Gauss-Legendre).
+#pragma once
+#include "acro_fastquad.cuh"
+
+namespace acro {
+
+constexpr int kTT = 20;         // temperatures per tile (accumulators per thread)
+constexpr int kPanN = 16;       // Gauss-Legendre nodes per panel
+constexpr int kMaxPan = 28;     // panels per point (12 fine + 12 coarse for a 2-decade T range; 17 + 11 for 4 decades)
+constexpr int kSharedThreads = 256;
+
+__constant__ double c_leg_modal[kPanN][kPanN];   // (2j+1)/2 * w_m * P_j(x_m): Legendre coefficients from nodal values
+__constant__ double c_leg_rec[kPanN][2];         // recurrence P_{j+1} = a_j t P_j - b_j P_{j-1}: a_j = (2j+1)/(j+1), b_j = j/(j+1)
+
+struct SharedGrid {
+    double y_top;     // top of the grid
+    int n_fine, n_pan;
+    double y_bot;     // bottom of the grid
+};
+
+// the grid of one model point (uniform over the block and identical in both kernels)
+__device__ __forceinline__ SharedGrid shared_grid(double Tmin, double Tmax, double E_top, double Ephb_T_max) {
+    SharedGrid g;
+    g.y_top = log(fmin(Ephb_T_max * Tmax, E_top));
+    const double y_split = log(Tmin) - 1.0, y_want = log(Tmin) - 25.0;
+    int nf = (int)ceil(g.y_top - y_split);
+    nf = max(1, min(nf, kMaxPan - 1));
+    int nc = (int)ceil(0.5 * (g.y_top - (double)nf - y_want));
+    nc = max(1, min(nc, kMaxPan - nf));
+    g.n_fine = nf;
+    g.n_pan = nf + nc;
+    g.y_bot = g.y_top - (double)nf - 2.0 * (double)nc;
+    return g;
+}
+
+// panel pn counted from the top: lower edge and width
+__device__ __forceinline__ void panel_geom(const SharedGrid& g, int pn, double& lo, double& h) {
+    if (pn < g.n_fine) { h = 1.0; lo = g.y_top - (double)(pn + 1); }
+    else { h = 2.0; lo = g.y_top - (double)g.n_fine - 2.0 * (double)(pn - g.n_fine + 1); }
+}
+
+// (pair, T) combinations served by the shared grid; evaluated identically by producer and consumer
+__device__ __forceinline__ bool shared_regime(double x_a, double x_b0, double T, double Ephb_T_max, double x_grid_bot, double T_min) {
+    (void)x_b0; (void)Ephb_T_max;
+    return (x_a <= kSteepX * T) && (x_a >= x_grid_bot || x_grid_bot <= 2e-11 * T_min);
+}
+
+struct PairLimits {           // T-independent limits of the three integrals of one pair; x_a < 0 marks "no range"
+    double xa9, xb9, xa10, xb10, xa11, xb11;
+};
+
+__device__ __forceinline__ PairLimits pair_limits(double E, double Ep) {
+    PairLimits L;
+    L.xa9 = L.xa10 = L.xa11 = -1.0;
+    L.xb9 = L.xb10 = L.xb11 = 0.0;
+    const double dE = Ep - E, ub = Ep - kMe2 / (4.0 * Ep);
+    if (!(Ep < E + kMe)) { L.xa9 = 0.25 * kMe2 * E / (Ep * Ep - Ep * E); L.xb9 = fmin(E, ub); }
+    if (E != Ep) {
+        const double pf = 0.25 * kMe2 / Ep - E, qf = 0.25 * kMe2 * dE / Ep;
+        const double sq = sqrt((0.5 * pf) * (0.5 * pf) - qf);
+        L.xa10 = -0.5 * pf - sq; L.xb10 = fmin(-0.5 * pf + sq, ub);
+    }
+    {
+        const double rt = sqrt(E * E - kMe2), den = 4.0 * Ep * dE + kMe2;
+        const double z1 = Ep * (kMe2 - 2.0 * dE * (rt - E)) / den, z2 = Ep * (kMe2 + 2.0 * dE * (rt + E)) / den;
+        L.xa11 = fmax(kMe2 / Ep, z1); L.xb11 = fmin(z2, Ep);
+    }
+    return L;
+}
+
+// Legendre moments of f over [lo_y, hi_y] inside the panel [p_lo, p_lo+h] (accumulated into mu):
+//   mu_j += int_{lo_y}^{hi_y} f(y) P_j(t(y)) dy      with the panel coordinate t in [-1, 1]
+template <int KIND>
+__device__ __forceinline__ void add_moments(const PairConst& c, double x_a, double lna, double lo_y, double hi_y, double p_lo,
+                                            double h, double mu[kPanN]) {
+    const double hp = 0.5 * (hi_y - lo_y), mp = 0.5 * (hi_y + lo_y);
+    const double ic = 2.0 / h, mid = p_lo + 0.5 * h;
+#pragma unroll 1
+    for (int s = 0; s < kPanN; ++s) {
+        const double y = fma(hp, c_glx[gl_offset(kPanN) + s], mp);
+        const double x = fexp(y);
+        double f;
+        if (KIND == KIND_IC_PHOTON) f = integrand_core<KIND_IC_PHOTON>(c, x, x_a, y - lna, true);
+        else if (KIND == KIND_IC_ELECTRON) f = integrand_core<KIND_IC_ELECTRON>(c, x, x_a, 0.0, false);
+        else f = integrand_core<KIND_PC_ELECTRON>(c, x, x_a, 0.0, false) * frcp(x);
+        f *= c_glw[gl_offset(kPanN) + s] * hp;
+        const double tt = (y - mid) * ic;
+        double pm = 1.0, pc = tt;
+        mu[0] += f;
+        mu[1] = fma(f, tt, mu[1]);
+#pragma unroll
+        for (int j = 1; j < kPanN - 1; ++j) {
+            const double pnx = fma(c_leg_rec[j][0] * tt, pc, -c_leg_rec[j][1] * pm);
+            pm = pc; pc = pnx;
+            mu[j + 1] = fma(f, pc, mu[j + 1]);
+        }
+    }
+}
+
+// int_{lo_y}^{hi_y} f(y) B(y) dy ~= sum_m nu[m] B(y_m), B = the degree-15 interpolant through the panel's nodes.
+// `y_layer` (or a value >= hi_y + 1 for "none"): position of a kinematic upper limit where the integrand has a boundary
+// layer much narrower than a panel (the electron kernel: q -> 1 within a few per cent of x_b0, peak at 1 - x/x_b0 ~ 0.03);
+// the interval is then cut at y_layer - 1/4 and y_layer - 1/16 so that the pieces are graded towards it.
+template <int KIND>
+__device__ __forceinline__ void partial_panel(const PairConst& c, double x_a, double lna, double lo_y, double hi_y, double p_lo,
+                                              double h, double y_layer, double nu[kPanN]) {
+    double mu[kPanN];
+#pragma unroll
+    for (int j = 0; j < kPanN; ++j) mu[j] = 0.0;
+    double from = lo_y;
+    const double c1 = y_layer - 0.25, c2 = y_layer - 0.0625;
+    if (c1 > from && c1 < hi_y) { add_moments<KIND>(c, x_a, lna, from, c1, p_lo, h, mu); from = c1; }
+    if (c2 > from && c2 < hi_y) { add_moments<KIND>(c, x_a, lna, from, c2, p_lo, h, mu); from = c2; }
+    add_moments<KIND>(c, x_a, lna, from, hi_y, p_lo, h, mu);
+#pragma unroll
+    for (int m = 0; m < kPanN; ++m) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < kPanN; ++j) v = fma(c_leg_modal[j][m], mu[j], v);
+        nu[m] = v;
+    }
+}
+
+__device__ __forceinline__ int panel_of(const SharedGrid& g, double y) {   // panel (from the top) that contains y
+    int pn;
+    if (y >= g.y_top - (double)g.n_fine) pn = (int)floor(g.y_top - y);
+    else pn = g.n_fine + (int)floor(0.5 * (g.y_top - (double)g.n_fine - y));
+    return max(0, min(pn, g.n_pan - 1));
+}
+
+// One integral of one pair on the shared grid for the kTT temperatures of the current tile.
+//   sx/six/sy: node tables x, 1/x, y;  sB: raw Bose values [node][kTT]
+// Range: [x_a, x_b0] clipped to the grid; the thermal cut-off 200 T is in the table (zeros above it).
+template <int KIND>
+__device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, double x_b0, const SharedGrid& g,
+                                                const double* __restrict__ sx, const double* __restrict__ six,
+                                                const double* __restrict__ sy, const double* __restrict__ sB, bool active,
+                                                double acc[kTT]) {
+#pragma unroll
+    for (int t = 0; t < kTT; ++t) acc[t] = 0.0;
+    double a = active ? flog(fmax(x_a, 1e-300)) : g.y_top;
+    const double lna = a;
+    double bb = active ? flog(x_b0) : g.y_top;
+    int p_first = -1, p_last = 0;     // lowest / highest panel touched (from the top: p_first >= p_last)
+    bool part_lo = false, part_hi = false;
+    if (active) {
+        if (a <= g.y_bot) { a = g.y_bot; p_first = g.n_pan - 1; }
+        else { p_first = panel_of(g, a); part_lo = true; }
+        if (bb >= g.y_top) { bb = g.y_top; p_last = 0; }
+        else { p_last = panel_of(g, bb); part_hi = true; }
+        if (bb <= a) { p_first = -1; }                          // nothing inside the grid
+    }
+    const bool act = p_first >= 0;
+    int p_lo = p_first;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p_lo = max(p_lo, __shfl_xor_sync(0xffffffffu, p_lo, o));
+    for (int pn = p_lo; pn >= 0; --pn) {
+        double lo, h;
+        panel_geom(g, pn, lo, h);
+        const bool inside = act && pn <= p_first && pn >= p_last;
+        // panels integrated through Legendre moments on their own nodes: the ones cut by a limit, and -- for the electron
+        // kernel -- the full panel just below a kinematic upper limit (its boundary layer can reach into it)
+        const bool layer = (KIND == KIND_IC_ELECTRON) && part_hi;
+        const bool is_part = inside && ((part_lo && pn == p_first) || (part_hi && pn == p_last) || (layer && pn == p_last + 1));
+        const bool full = inside && !is_part;
+        const int base = pn * kPanN;
+        if (!__any_sync(0xffffffffu, inside)) continue;
+        if (__any_sync(0xffffffffu, is_part)) {
+            double nu[kPanN];
+#pragma unroll
+            for (int m = 0; m < kPanN; ++m) nu[m] = 0.0;
+            if (is_part) {
+                const double lo_y = (part_lo && pn == p_first) ? a : lo;
+                const double hi_y = (part_hi && pn == p_last) ? bb : lo + h;
+                partial_panel<KIND>(c, x_a, lna, lo_y, hi_y, lo, h, layer ? bb : hi_y + 2.0, nu);
+            }
+#pragma unroll
+            for (int m = 0; m < kPanN; ++m) {
+                const double* __restrict__ Bk = sB + (size_t)(base + m) * kTT;
+                const double v = nu[m];
+#pragma unroll
+                for (int t = 0; t < kTT; ++t) acc[t] = fma(v, Bk[t], acc[t]);
+            }
+        }
+        if (__any_sync(0xffffffffu, full)) {
+            const double wscale = 0.5 * h;
+#pragma unroll 1
+            for (int m = 0; m < kPanN; ++m) {
+                const int k = base + m;
+                double f = 0.0;
+                if (full) {
+                    const double x = sx[k];
+                    if (KIND == KIND_IC_PHOTON) {
+                        const double q = x_a * six[k];
+                        const double omq = 1.0 - q;
+                        f = fma(2.0 * q, lna - sy[k], fma(fma(2.0, q, 1.0), omq, c.c9 * omq));
+                    } else if (KIND == KIND_IC_ELECTRON) {
+                        f = integrand_core<KIND_IC_ELECTRON>(c, x, x_a, 0.0, false);
+                    } else {   // the table holds x^2/(e^{x/T}-1); the pair-creation integrand carries x^1
+                        f = integrand_core<KIND_PC_ELECTRON>(c, x, x_a, 0.0, false) * six[k];
+                    }
+                    f *= c_glw[gl_offset(kPanN) + m] * wscale;
+                }
+                const double* __restrict__ Bk = sB + (size_t)k * kTT;
+#pragma unroll
+                for (int t = 0; t < kTT; ++t) acc[t] = fma(f, Bk[t], acc[t]);
+            }
+        }
+    }
+}
+
+// Producer kernel: grid (pair tiles, points), kSharedThreads threads, dynamic shared memory.
+__global__ void __launch_bounds__(kSharedThreads, 2) kernels_shared_kernel(acro_batch_t b, double* __restrict__ Kws, acro_params_t p) {
+    extern __shared__ double sm[];
+    const int pt = blockIdx.y;
+    const int ne = b.pt_ne[pt], nt = b.pt_nt[pt], s0 = b.pt_sys_off[pt];
+    const int64_t tri = (int64_t)ne * (ne + 1) / 2;
+    const int64_t loc0 = (int64_t)blockIdx.x * kSharedThreads;
+    if (loc0 >= tri) return;
+    const double* eg = b.e_grid + b.pt_e_off[pt];
+    const double Tmin = b.sys_T[s0], Tmax = b.sys_T[s0 + nt - 1];
+    const SharedGrid g = shared_grid(Tmin, Tmax, eg[ne - 1], p.Ephb_T_max);
+    const int nn = g.n_pan * kPanN;
+    double* sx = sm;
+    double* six = sx + kMaxPan * kPanN;
+    double* sy = six + kMaxPan * kPanN;
+    double* sB = sy + kMaxPan * kPanN;                 // [nn][kTT]
+    for (int k = threadIdx.x; k < nn; k += blockDim.x) {
+        double lo, h;
+        panel_geom(g, k / kPanN, lo, h);
+        const double y = lo + 0.5 * h * (1.0 + c_glx[gl_offset(kPanN) + (k % kPanN)]);
+        const double x = fexp(y);
+        sy[k] = y; sx[k] = x; six[k] = frcp(x);
+    }
+    // this thread's pair
+    const int64_t loc = loc0 + threadIdx.x;
+    const bool active = loc < tri;
+    int i = 0, j = 0;
+    if (active) {
+        const double tn = 2.0 * ne + 1.0;
+        i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+        i = max(0, min(i, ne - 1));
+        while (i > 0 && tri_row_off(i, ne) > loc) --i;
+        while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
+        j = i + (int)(loc - tri_row_off(i, ne));
+    }
+    const double E = eg[i], Ep = eg[j];
+    PairConst c;
+    c.E = E; c.Ep = Ep; c.dE = Ep - E;
+    {
+        const double r = E / fmax(c.dE, 1e-300);
+        c.c9 = r * r / (2.0 + 2.0 * r);
+        c.c10 = 0.25 * kMe2 / Ep;
+        c.i2Ep = 0.5 / Ep;
+    }
+    const PairLimits L = pair_limits(E, Ep);
+    const double x_bot = exp(g.y_bot);
+    const int64_t np = b.n_pairs_total;
+    for (int t0 = 0; t0 < nt; t0 += kTT) {
+        __syncthreads();
+        // Bose table of this temperature tile: raw x^2/(pi^2 (e^{x/T}-1)), zero above the cut-off 200 T
+        for (int idx = threadIdx.x; idx < nn * kTT; idx += blockDim.x) {
+            const int k = idx / kTT, t = idx % kTT;
+            double v = 0.0;
+            if (t0 + t < nt) {
+                const double T = b.sys_T[s0 + t0 + t];
+                const double x = sx[k];
+                if (x <= p.Ephb_T_max * T) v = x * x * bose_inv(x / T) * (1.0 / kPi2);
+            }
+            sB[idx] = v;
+        }
+        __syncthreads();
+        double acc[kTT];
+        // e -> gamma
+        {
+            const bool act = active && L.xa9 > 0.0 && L.xb9 > L.xa9;
+            shared_integral<KIND_IC_PHOTON>(c, L.xa9, L.xb9, g, sx, six, sy, sB, act, acc);
+            if (act)
+                for (int t = 0; t < kTT && t0 + t < nt; ++t) {
+                    const double T = b.sys_T[s0 + t0 + t];
+                    if (shared_regime(L.xa9, L.xb9, T, p.Ephb_T_max, x_bot, Tmin)) Kws[1 * np + b.sys_k_off[s0 + t0 + t] + loc] = acc[t];
+                }
+        }
+        // e -> e
+        {
+            const bool act = active && L.xa10 > 0.0 && L.xb10 > L.xa10;
+            shared_integral<KIND_IC_ELECTRON>(c, L.xa10, L.xb10, g, sx, six, sy, sB, act, acc);
+            if (act)
+                for (int t = 0; t < kTT && t0 + t < nt; ++t) {
+                    const double T = b.sys_T[s0 + t0 + t];
+                    if (shared_regime(L.xa10, L.xb10, T, p.Ephb_T_max, x_bot, Tmin)) Kws[4 * np + b.sys_k_off[s0 + t0 + t] + loc] = acc[t];
+                }
+        }
+        // gamma -> e (pair creation): integrand G * x / (e^{x/T}-1) = (G/x) * x^2 / (...): the table holds x^2
+        {
+            const bool act = active && L.xa11 > 0.0 && L.xb11 > L.xa11;
+            shared_integral<KIND_PC_ELECTRON>(c, L.xa11, L.xb11, g, sx, six, sy, sB, act, acc);
+            if (act)
+                for (int t = 0; t < kTT && t0 + t < nt; ++t) {
+                    const double T = b.sys_T[s0 + t0 + t];
+                    if (!(Ep < kMe2 / (50.0 * T)) && shared_regime(L.xa11, L.xb11, T, p.Ephb_T_max, x_bot, Tmin))
+                        Kws[3 * np + b.sys_k_off[s0 + t0 + t] + loc] = acc[t];
+                }
+        }
+    }
+}
+
+}  // namespace acro

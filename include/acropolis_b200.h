@@ -54,8 +54,10 @@ extern "C" {
 #define ACRO_ST_E0_ABOVE_GEV  8  /* injection energy > 1 GeV ("results cannot be trusted")                   */
 
 /* how the three thermal kernel integrals are evaluated (same integrals and limits either way) */
-#define ACRO_KERNELS_FAST      0  /* Gauss-Laguerre on the Wien tail, reduced integrands, division-free (default) */
+#define ACRO_KERNELS_FAST      0  /* temperature-shared panel grid (Bose table in shared memory) + Gauss-Laguerre on the Wien
+                                     tail + reduced Gauss-Legendre elsewhere (default)                                */
 #define ACRO_KERNELS_PLAIN_GL  1  /* plain Q-point Gauss-Legendre in log(eps_bar) with the reference's F/G incl. range tests */
+#define ACRO_KERNELS_PER_T     2  /* as FAST but every (pair,T) integral evaluated on its own (no temperature sharing)    */
 
 /* continuous-source representation */
 #define ACRO_SC_NONE       0  /* SC == 0 for all species (models.py:197-206 defaults)                        */

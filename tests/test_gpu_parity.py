@@ -207,8 +207,9 @@ def test_linearity_in_sources(gpu_engine, results):
     live = r["F"] > 1e-190
     assert np.array_equal(F2[live], 8.0 * r["F"][live])
     live = r["pdi"] > 1e-45      # rates fed by floored (1e-200) spectrum values do not scale
-    assert np.allclose(r2["pdi"][live], 8.0 * r["pdi"][live], rtol=1e-13, atol=0)
-    assert np.allclose(r2["mpdi"][0], 8.0 * r["mpdi"][0], rtol=1e-12, atol=0)
+    # exp(m*y + b) with |b| ~ 100: one ulp of the exponent is ~1e-14 relative
+    assert np.allclose(r2["pdi"][live], 8.0 * r["pdi"][live], rtol=1e-10, atol=0)
+    assert np.allclose(r2["mpdi"][0], 8.0 * r["mpdi"][0], rtol=1e-10, atol=0)
 
 
 def test_c_abi_host_entry(gpu_engine, results):
