@@ -50,6 +50,7 @@ class _Arena(object):
         self.device = device
         self.host = None
         self.dev = None
+        self.busy = None     # event after the last H2D from this arena's pinned buffer
 
     def upload(self, arrays, stream):
         offs, total = [], 0
@@ -67,6 +68,8 @@ class _Arena(object):
                 hv[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
         with torch.cuda.stream(stream):
             self.dev[:total].copy_(self.host[:total], non_blocking=True)
+            self.busy = torch.cuda.Event()
+            self.busy.record(stream)
         base = self.dev.data_ptr()
         return [base + o for o in offs], total
 
@@ -245,12 +248,32 @@ class Engine(object):
             self._collect(pnd, res)
         return {k: (np.concatenate(v) if v else np.zeros(0)) for k, v in res.items()}
 
+    def submit(self, points, stages=_lib.STAGE_ALL, want=("Yf", "status"), budget=None):
+        """Stage and launch `points` (split by the workspace budget) without waiting; returns pending handles for
+        ``collect``.  Lets the caller prepare the next group of points on the host while the GPU works."""
+        self._sync_params()
+        pend = []
+        for idx in self.chunks(points, budget):
+            ch = self.stage([points[i] for i in idx], want)
+            self.launch(ch, stages)
+            pend.append(self.fetch(ch, want))
+        return pend
+
+    def collect(self, pending, want=("Yf", "status")):
+        """Wait for pending handles of ``submit`` and return the concatenated outputs."""
+        res = {k: [] for k in want}
+        for pnd in pending:
+            self._collect(pnd, res)
+        return {k: (np.concatenate(v) if v else np.zeros(0)) for k, v in res.items()}
+
     def stage(self, pts, want=("Yf", "status"), resident=False):
         """Assemble a chunk on the host, copy it to the device (one pinned H2D) and allocate its outputs.  With
         ``resident`` the chunk gets its own device buffers (it can be launched repeatedly, e.g. by the benchmark)."""
         a, cnt = self.assemble(pts)
         st = self.stream
         arena = _Arena(self.device) if resident else self._arena_for_chunk()
+        if not resident and arena.busy is not None:
+            arena.busy.synchronize()      # the copy that last used this staging buffer must have finished
         ptrs, nbytes = arena.upload([a[k] for k in self._ORDER], st)
         self.last_h2d_bytes = getattr(self, "last_h2d_bytes", 0) + nbytes
         b = _lib.Batch()
@@ -310,8 +333,8 @@ class Engine(object):
     def _arena_for_chunk(self):
         # two arenas alternate so that chunk n+1 can be staged while chunk n is still being read by the GPU
         if not hasattr(self, "_arenas"):
-            self._arenas, self._arena_i = [_Arena(self.device), _Arena(self.device)], 0
-        self._arena_i ^= 1
+            self._arenas, self._arena_i = [_Arena(self.device) for _ in range(4)], 0
+        self._arena_i = (self._arena_i + 1) % len(self._arenas)
         return self._arenas[self._arena_i]
 
     def _collect(self, pnd, res):

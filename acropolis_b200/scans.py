@@ -145,13 +145,55 @@ def run_models(models, devices=None, want_matp=False):
     return (Yf, matp) if want_matp else Yf
 
 
-def run_points(model, param_sets, devices=None):
+def run_points(model, param_sets, devices=None, group=256):
     """Rows ``[sorted params..., 9 mean, 9 high, 9 low]`` for an arbitrary list of parameter dicts of one model class
     (or ``functools.partial``): the batched form of ``BufferedScanner._run_single`` (reference scans.py:110-124).
-    Builds the models, stages their grids and source arrays, runs the CUDA path and reads the abundances back."""
-    models = [model(**p) for p in param_sets]
-    Yf = run_models(models, devices=devices)
-    return np.array([[*[p[k] for k in sorted(p)], *Y.transpose().reshape(Y.size)] for p, Y in zip(param_sets, Yf)])
+    Builds the models, stages their grids and source arrays, runs the CUDA path and reads the abundances back.  On one
+    device the list is processed in groups of `group` points: while the GPU works on one group the host constructs the
+    models and source arrays of the next."""
+    import torch
+    if devices is None:
+        dist = _dist_world()
+        devices = [torch.cuda.current_device()] if dist is not None else list(range(max(1, torch.cuda.device_count())))
+    devices = list(devices)
+    N = len(param_sets)
+    if len(devices) != 1 or N == 0:
+        models = [model(**p) for p in param_sets]
+        Yf = run_models(models, devices=devices)
+        return np.array([[*[p[k] for k in sorted(p)], *Y.transpose().reshape(Y.size)] for p, Y in zip(param_sets, Yf)])
+    rows, eng, in_flight = [None] * N, None, []
+
+    def finish(entry):
+        idx, pend = entry
+        out = eng.collect(pend, want=("Yf", "status"))
+        for k, i in enumerate(idx):
+            Y = out["Yf"][k][:, :ncol]
+            p = param_sets[i]
+            rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
+
+    ncol = 3
+    for g0 in range(0, N, group):
+        idx, specs = [], []
+        for i in range(g0, min(g0 + group, N)):
+            m = model(**param_sets[i])
+            ncol = m._sII.bbn_abundances().shape[1]
+            if m.is_trivial():
+                Y = m._squeeze_decays(m._sII.bbn_abundances())
+                p = param_sets[i]
+                rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
+            else:
+                if eng is None:
+                    eng = Engine.get(m._sII, devices[0])
+                    eng.last_h2d_bytes = eng.last_d2h_bytes = 0
+                idx.append(i)
+                specs.append(m.point_spec())
+        if specs:
+            in_flight.append((idx, eng.submit(specs, want=("Yf", "status"))))
+        while len(in_flight) > 2:
+            finish(in_flight.pop(0))
+    for entry in in_flight:
+        finish(entry)
+    return np.array(rows)
 
 
 class BufferedScanner(object):
@@ -227,10 +269,8 @@ class BufferedScanner(object):
         mine = np.arange(N)
         if world > 1:   # cheap cost proxy before any model is built: the E0-dependent grid size is not known here,
             mine = np.arange(rank, N, world)   # so deal points round-robin (neighbouring points cost the same)
-        models = [self._build(pts[i]) for i in mine]
-        Yf = run_models(models, devices=devices)
-        rows = np.array([self._row(pts[i], Yf[k]) for k, i in enumerate(mine)]).reshape(len(mine), -1)
-        width = 2 + Yf.shape[1] * Yf.shape[2]
+        rows = run_points(lambda **sp: self._build(sp), [pts[i] for i in mine], devices=devices).reshape(len(mine), -1)
+        width = rows.shape[1] if len(mine) else 29
         return gather_rows(mine, rows, N, width) if world > 1 else rows
 
     # -- one fast parameter: full computation for the first fast value, rescaled mpdi for the rest (scans.py:127-176)
