@@ -24,6 +24,10 @@ namespace acro {
 // ------------------------------------------------------------------------------------------------------------
 // Gauss-Legendre tables in constant memory: orders 8, 16, 32, 64, 96, 128 packed back to back.
 // ------------------------------------------------------------------------------------------------------------
+// cross-section tables of sigma_rt (filled by upload_quadrature_tables)
+__constant__ double c_sig[ACRO_NR][4];    // generic reactions: {log(N Q^p1), p2, p3, Q}
+__constant__ double c_sig2[2][3];         // second power-law terms of reactions 13 and 16: {log(N Q^p1), p2, p3}
+
 constexpr int kGLTotal = 8 + 16 + 32 + 64 + 96 + 128;
 __constant__ double c_glx[kGLTotal];
 __constant__ double c_glw[kGLTotal];
@@ -109,6 +113,25 @@ cudaError_t upload_quadrature_tables() {
         }
     }
     for (int j = 0; j < kPanN; ++j) { rec[j][0] = (2.0 * j + 1.0) / (j + 1.0); rec[j][1] = (double)j / (j + 1.0); }
+    {   // cross-section tables (nucl.py:217-347): {log(N Q^p1), p2, p3, Q}
+        static const double gen[ACRO_NR][4] = {   // N, p1, p2, p3 (reactions with their own formula: N = 1, p = 0)
+            {1, 0, 0, 0}, {9.8, 1.95, 1.65, 3.6}, {26.0, 2.6, 2.3, 4.9}, {8.88, 1.75, 1.65, 3.4}, {16.7, 1.95, 2.3, 4.25},
+            {19.5, 3.5, 1.0, 4.5}, {20.7, 3.5, 1.0, 4.5}, {10.7, 10.2, 3.4, 13.6}, {21.7, 4.0, 3.0, 7.0}, {143.0, 2.3, 4.7, 7.0},
+            {38.1, 3.0, 2.0, 5.0}, {1, 0, 0, 0}, {0.176, 1.51, 0.49, 2.0}, {122.0, 4.0, 3.0, 7.0}, {1, 0, 0, 0},
+            {32.6, 10.0, 2.0, 12.0}, {133.0, 4.0, 3.0, 7.0}};
+        static const double eth[ACRO_NR] = {2.224573, 6.257248, 8.481821, 5.493485, 7.718058, 19.813852, 20.577615, 23.846527,
+                                            26.071100, 3.698892, 15.794685, 2.467032, 7.249962, 10.948850, 1.586627, 5.605794,
+                                            9.304680};
+        double sig[ACRO_NR][4], sig2[2][3];
+        for (int r = 0; r < ACRO_NR; ++r) {
+            sig[r][0] = std::log(gen[r][0]) + gen[r][1] * std::log(eth[r]);
+            sig[r][1] = gen[r][2]; sig[r][2] = gen[r][3]; sig[r][3] = eth[r];
+        }
+        sig2[0][0] = std::log(1205.0) + 5.5 * std::log(eth[12]); sig2[0][1] = 5.0; sig2[0][2] = 10.5;
+        sig2[1][0] = std::log(2.27e6) + 8.8335 * std::log(eth[15]); sig2[1][1] = 13.0; sig2[1][2] = 21.8335;
+        if ((e = cudaMemcpyToSymbol(c_sig, sig, sizeof(sig))) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbol(c_sig2, sig2, sizeof(sig2))) != cudaSuccess) return e;
+    }
     if ((e = cudaMemcpyToSymbol(c_leg_modal, modal, sizeof(modal))) != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_leg_rec, rec, sizeof(rec));
 }
@@ -543,6 +566,47 @@ __global__ void unpack_kernels_kernel(const double* __restrict__ Kws, int64_t np
 // F_gamma the log-log interpolant of the grid values (nucl.py:398-467, utils.py:38-61), integrated exactly cell
 // by cell (GL-8 per cell; the threshold cell with a quadratic substitution) instead of adaptive QAGS.
 // ------------------------------------------------------------------------------------------------------------
+// Cross-sections in mb for a RUN-TIME reaction index (one copy of the code: the 17-way inlined version made the solve
+// kernel ~290 kB of SASS and instruction-cache bound, ncu: 8 warps stalled on no_instruction per issue).  Same formulas
+// as cross_section_mb (acro_physics.cuh); power laws as exp(c + p2 log(E-Q) - p3 log E) with the fast exp/log.
+
+__device__ __noinline__ double sigma_rt(int r, double E, double lnE) {   // r = 0..16
+    const double Q = c_sig[r][3];
+    if (!(E > Q)) return 0.0;
+    const double lt = flog(E - Q);
+    const double gen = fexp(fmax(c_sig[r][0] + c_sig[r][1] * lt - c_sig[r][2] * lnE, -700.0));
+    switch (r) {
+        case 0: {   // d+a>n+p
+            const double rr = sqrt(Q * (E - Q)) / E;
+            const double sq = sqrt(Q) - sqrt(0.037);
+            return 18.75 * (rr * rr * rr + 0.007947 * (rr * rr) * (sq * sq / (E - Q + 0.037)));
+        }
+        case 10: {  // Li6+a>X
+            const double g1 = (E - 19.0) / 3.5, g2 = (E - 30.0) / 3.0, g3 = (E - 43.0) / 5.0;
+            return gen * (3.7 * exp(-0.5 * g1 * g1) + 2.75 * exp(-0.5 * g2 * g2) + 2.2 * exp(-0.5 * g3 * g3));   // exp: may underflow
+        }
+        case 11: {  // Li7+a>t+He4
+            const double Ecm = E - Q, e2 = Ecm * Ecm;
+            const double pp = 1.0 + 2.2875 * e2 - 1.1798 * (e2 * Ecm) + 2.5279 * (e2 * e2);
+            return 0.105 * (2371.0 / (E * E)) * exp(-2.5954 / sqrt(Ecm) - 2.056 * Ecm) * pp;
+        }
+        case 12: {  // Li7+a>n+Li6
+            const double z = (E - Q - 7.46) / 0.188;
+            return gen + fexp(fmax(c_sig2[0][0] + c_sig2[0][1] * lt - c_sig2[0][2] * lnE, -700.0)) + 0.06 / (1.0 + z * z);
+        }
+        case 14: {  // Be7+a>He3+He4
+            const double Ecm = E - Q, e2 = Ecm * Ecm;
+            const double pp = 1.0 - 0.428 * e2 + 0.534 * (e2 * Ecm) - 0.115 * (e2 * e2);
+            if (pp < 0.0) return 0.0;
+            return 0.504 * (2371.0 / (E * E)) * exp(-5.1909 / sqrt(Ecm) - 0.548 * Ecm) * pp;
+        }
+        case 15:    // Be7+a>p+Li6
+            return gen + fexp(fmax(c_sig2[1][0] + c_sig2[1][1] * lt - c_sig2[1][2] * lnE, -700.0));
+        default:
+            return gen;
+    }
+}
+
 __device__ __forceinline__ void solve3(double B[3][3], double a[3], double x[3]) {
     // Gaussian elimination with partial pivoting (the reference calls LAPACK dgesv, cascade.py:221)
     int p[3] = {0, 1, 2};
@@ -669,9 +733,8 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
     const int nq = p.pdi_cell_order;   // 8 or 16
     const double* qx = c_glx + gl_offset(nq);
     const double* qw = c_glw + gl_offset(nq);
-    double acc[ACRO_NR];
-#pragma unroll
-    for (int r = 0; r < ACRO_NR; ++r) acc[r] = 0.0;
+    double* accs = lnE + ne;             // [17][32] per-lane accumulators in shared memory (run-time reaction index)
+    for (int r = 0; r < ACRO_NR; ++r) accs[r * 32 + lane] = 0.0;
     // (A) cells that lie entirely above a reaction's threshold: nodes shared by all reactions
     for (int c = lane; c < ne - 1; c += 32) {
         const double y0 = lnE[c], y1 = lnE[c + 1];
@@ -691,16 +754,23 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
         const int nsub = max(1, (int)ceil(0.5 * fabs(kap) * len));
         const double piece = len / (double)nsub;
         const double start = (kap > 0.0) ? hi - len : y0;      // pieces cover [start, start + len]
+        int r_hi = 0;                                          // reactions 0..r_hi-1 are open in this cell? (not sorted) -> mask
+        unsigned open = 0;
+        for (int r = 0; r < ACRO_NR; ++r)
+            if (kEth[r] <= Elo && !(r == 14 && kink_cell)) open |= 1u << r;
+        (void)r_hi;
+        if (!open) continue;
         for (int q = 0; q < nsub; ++q) {
             const double a = start + piece * (double)q;
             const double h = 0.5 * piece, m = a + h;
+#pragma unroll 1
             for (int k = 0; k < nq; ++k) {
                 const double y  = fma(h, qx[k], m);
-                const double Ev = exp(y);
+                const double Ev = fexp(y);
                 const double fe = qw[k] * h * exp(fma(kap, y, bs));
-#pragma unroll
+#pragma unroll 1
                 for (int r = 0; r < ACRO_NR; ++r)
-                    if (kEth[r] <= Elo && !(r == 14 && kink_cell)) acc[r] = fma(fe, cross_section_mb(r + 1, Ev, y), acc[r]);
+                    if (open & (1u << r)) accs[r * 32 + lane] = fma(fe, sigma_rt(r, Ev, y), accs[r * 32 + lane]);
             }
         }
     }
@@ -727,7 +797,7 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
                     const double u  = 0.5 * (1.0 + tx[k]);
                     const double y  = fma(hi - lo, u * u, lo);
                     const double Ev = exp(y);
-                    thr = fma(tw[k] * 0.5 * (hi - lo) * 2.0 * u * exp(fma(ms, y, bs)) * Ev, cross_section_mb(lane + 1, Ev, y), thr);
+                    thr = fma(tw[k] * 0.5 * (hi - lo) * 2.0 * u * exp(fma(ms, y, bs)) * Ev, sigma_rt(lane, Ev, y), thr);
                 }
             }
         }
@@ -752,19 +822,20 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
                 for (int k = 0; k < 16; ++k) {
                     const double y  = fma(h, tx[k], m);
                     const double Ev = exp(y);
-                    thr = fma(tw[k] * h * exp(fma(ms + 1.0, y, bs)), cross_section_mb(15, Ev, y), thr);
+                    thr = fma(tw[k] * h * exp(fma(ms + 1.0, y, bs)), sigma_rt(14, Ev, y), thr);
                 }
             }
         }
     }
     const double rate_E0 = g[top];   // Gamma_gamma(E0, T): the grid's last point is E0 (cascade.py:745, nucl.py:436)
-#pragma unroll
+    const double lnE0 = log(E0);
+#pragma unroll 1
     for (int r = 0; r < ACRO_NR; ++r) {
-        double v = warp_sum(acc[r]);
+        double v = warp_sum(accs[r * 32 + lane]);
         v += __shfl_sync(0xffffffffu, thr, r);
         if (r == 14) v += __shfl_sync(0xffffffffu, thr, ACRO_NR);
         if (lane == 0) {
-            double rate = S0[0] * cross_section(r + 1, E0) / rate_E0;
+            double rate = S0[0] * kMbToIMeV2 * sigma_rt(r, E0, lnE0) / rate_E0;
             if (Emax > kEth[r]) rate += kMbToIMeV2 * v;
             pdi[(int64_t)s * ACRO_NR + r] = fmax(p.approx_zero, rate);
         }
@@ -1131,7 +1202,7 @@ cudaError_t launch_solve_pdi(const acro_batch_t& b, const acro_out_t& o, const D
                              const double* Kws, cudaStream_t st, LaunchCounters& lc) {
     (void)t;
     if (b.n_systems == 0) return cudaSuccess;
-    const int stride = 5 * b.ne_max;                           // doubles per warp
+    const int stride = 5 * b.ne_max + ACRO_NR * 32;            // doubles per warp: wF[3][ne], lnF, lnE, pdi accumulators
     int wpb = 4;
     while (wpb > 1 && (size_t)wpb * stride * sizeof(double) > 200 * 1024) wpb >>= 1;
     const size_t smem = (size_t)wpb * stride * sizeof(double);
