@@ -24,9 +24,10 @@
 
 namespace acro {
 
-__constant__ double c_lag_s[24];    // Gauss-Laguerre nodes, n = 24
-__constant__ double c_lag_w[24];    // weights (include e^{-s})
-__constant__ double c_lag_es[24];   // e^{-s_k}
+// Gauss-Laguerre rules n = 12, 16, 24 packed back to back (offsets 0, 12, 28): nodes, weights (include e^{-s}), e^{-s_k}
+__constant__ double c_lag_s[52];
+__constant__ double c_lag_w[52];
+__constant__ double c_lag_es[52];
 
 __constant__ double c_half_range = 8.0;           // log-range [e-folds] up to which Q/2 nodes are used (a9, a11 only)
 constexpr double kSteepX = 2.718281828459045;   // x_a/T above which the Laguerre form is used (u_a > 1)
@@ -142,11 +143,15 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
     const double iT = 1.0 / T;
     const double va = x_a * iT;
     if (va > kSteepX && (x_b - x_a) * iT >= kSteepSpan) {
-        // Gauss-Laguerre in s = (x - x_a)/T
+        // Gauss-Laguerre in s = (x - x_a)/T.  The further out on the Wien tail, the smoother the integrand on the scale of
+        // the weight: 24 nodes for e < x_a/T <= e^1.5, 16 up to e^2, 12 beyond (prototype: <= 6e-11 in each band).
         const double Ea = fexp(-va);
+        const int n = (va > 7.38905609893065) ? 12 : ((va > 4.4816890703380645) ? 16 : 24);
+        const int off = (n == 12) ? 0 : ((n == 16) ? 12 : 28);
         double sum = 0.0;
 #pragma unroll 1
-        for (int k = 0; k < 24; ++k) {
+        for (int kk = 0; kk < n; ++kk) {
+            const int k = off + kk;
             const double x = fma(c_lag_s[k], T, x_a);
             if (x < x_b) {
                 double g = integrand_core<KIND>(c, x, x_a, 0.0, false);

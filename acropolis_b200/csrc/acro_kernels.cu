@@ -93,9 +93,11 @@ cudaError_t upload_quadrature_tables() {
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_glw, w.data(), sizeof(double) * kGLTotal);
     if (e != cudaSuccess) return e;
-    double ls[24], lw[24], les[24];
-    gauss_laguerre(24, ls, lw);
-    for (int i = 0; i < 24; ++i) les[i] = std::exp(-ls[i]);
+    double ls[52], lw[52], les[52];
+    gauss_laguerre(12, ls, lw);
+    gauss_laguerre(16, ls + 12, lw + 12);
+    gauss_laguerre(24, ls + 28, lw + 28);
+    for (int i = 0; i < 52; ++i) les[i] = std::exp(-ls[i]);
     if ((e = cudaMemcpyToSymbol(c_lag_s, ls, sizeof(ls))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_lag_w, lw, sizeof(lw))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_lag_es, les, sizeof(les))) != cudaSuccess) return e;
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(128, ACRO_KK_MINBLOCKS) kernels_kernel(acro_ba
     KernelEntry k;
     if (FAST) {
         SharedInfo si;
-        si.on = (p.kernel_mode == ACRO_KERNELS_FAST);
+        si.on = false;   // per-(pair,T) evaluation only (ACRO_KERNELS_PER_T); the FAST mode runs kernels_shared_kernel instead
         const int s_first = b.pt_sys_off[pt], nt = b.pt_nt[pt];
         si.Tmin = b.sys_T[s_first];
         const SharedGrid g = shared_grid(si.Tmin, b.sys_T[s_first + nt - 1], eg[ne - 1], p.Ephb_T_max);
@@ -1163,20 +1165,29 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
             default: kernels_kernel<64, false><<<g, 128, 0, st>>>(b, Kws, t, p); break;
         }
     } else {
-        if (p.kernel_mode == ACRO_KERNELS_FAST) {   // temperature-shared producer (acro_tshared.cuh)
-            const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT);
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaError_t e = cudaFuncSetAttribute(kernels_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return e;
-                attr_set = true;
-            }
+        if (p.kernel_mode == ACRO_KERNELS_FAST) {   // the production kernel builder (acro_tshared.cuh): all five planes
+            const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT + 4 * kTT);
             const int64_t tri_max = (int64_t)b.ne_max * (b.ne_max + 1) / 2;
             dim3 grid((unsigned)((tri_max + kSharedThreads - 1) / kSharedThreads), (unsigned)b.n_points);
-            kernels_shared_kernel<<<grid, kSharedThreads, smem, st>>>(b, Kws, p);
-            lc.launches++;
-            cudaError_t e = cudaGetLastError();
+            cudaError_t e = cudaSuccess;
+            static bool attr_set = false;
+            if (!attr_set) {
+                e = cudaFuncSetAttribute(kernels_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set = (e == cudaSuccess);
+            }
             if (e != cudaSuccess) return e;
+            kernels_shared_kernel<<<grid, kSharedThreads, smem, st>>>(b, Kws, t, p);
+            lc.launches++;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            switch (p.quad_order) {
+                case 16: kernels_wien_kernel<16><<<g, 128, 0, st>>>(b, Kws, p); break;
+                case 32: kernels_wien_kernel<32><<<g, 128, 0, st>>>(b, Kws, p); break;
+                case 96: kernels_wien_kernel<96><<<g, 128, 0, st>>>(b, Kws, p); break;
+                default: kernels_wien_kernel<64><<<g, 128, 0, st>>>(b, Kws, p); break;
+            }
+            if (e != cudaSuccess) return e;
+            lc.launches++;
+            return cudaGetLastError();
         }
         switch (p.quad_order) {
             case 16: kernels_kernel<16, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;

@@ -23,7 +23,14 @@
 
 namespace acro {
 
+#ifndef ACRO_TS_UNROLL
+#define ACRO_TS_UNROLL 1
+#endif
+#ifndef ACRO_TS_HC
+#define ACRO_TS_HC 2.0
+#endif
 constexpr int kTT = 20;         // temperatures per tile (accumulators per thread)
+constexpr double kHC = ACRO_TS_HC;   // width of the coarse panels [e-folds]
 constexpr int kPanN = 16;       // Gauss-Legendre nodes per panel
 constexpr int kMaxPan = 28;     // panels per point (12 fine + 12 coarse for a 2-decade T range; 17 + 11 for 4 decades)
 constexpr int kSharedThreads = 256;
@@ -44,18 +51,18 @@ __device__ __forceinline__ SharedGrid shared_grid(double Tmin, double Tmax, doub
     const double y_split = log(Tmin) - 1.0, y_want = log(Tmin) - 25.0;
     int nf = (int)ceil(g.y_top - y_split);
     nf = max(1, min(nf, kMaxPan - 1));
-    int nc = (int)ceil(0.5 * (g.y_top - (double)nf - y_want));
+    int nc = (int)ceil((g.y_top - (double)nf - y_want) / kHC);
     nc = max(1, min(nc, kMaxPan - nf));
     g.n_fine = nf;
     g.n_pan = nf + nc;
-    g.y_bot = g.y_top - (double)nf - 2.0 * (double)nc;
+    g.y_bot = g.y_top - (double)nf - kHC * (double)nc;
     return g;
 }
 
 // panel pn counted from the top: lower edge and width
 __device__ __forceinline__ void panel_geom(const SharedGrid& g, int pn, double& lo, double& h) {
     if (pn < g.n_fine) { h = 1.0; lo = g.y_top - (double)(pn + 1); }
-    else { h = 2.0; lo = g.y_top - (double)g.n_fine - 2.0 * (double)(pn - g.n_fine + 1); }
+    else { h = kHC; lo = g.y_top - (double)g.n_fine - kHC * (double)(pn - g.n_fine + 1); }
 }
 
 // (pair, T) combinations served by the shared grid; evaluated identically by producer and consumer
@@ -143,7 +150,7 @@ __device__ __forceinline__ void partial_panel(const PairConst& c, double x_a, do
 __device__ __forceinline__ int panel_of(const SharedGrid& g, double y) {   // panel (from the top) that contains y
     int pn;
     if (y >= g.y_top - (double)g.n_fine) pn = (int)floor(g.y_top - y);
-    else pn = g.n_fine + (int)floor(0.5 * (g.y_top - (double)g.n_fine - y));
+    else pn = g.n_fine + (int)floor((g.y_top - (double)g.n_fine - y) / kHC);
     return max(0, min(pn, g.n_pan - 1));
 }
 
@@ -203,7 +210,7 @@ __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, 
         }
         if (__any_sync(0xffffffffu, full)) {
             const double wscale = 0.5 * h;
-#pragma unroll 1
+            ACRO_UNROLL(ACRO_TS_UNROLL)
             for (int m = 0; m < kPanN; ++m) {
                 const int k = base + m;
                 double f = 0.0;
@@ -228,8 +235,12 @@ __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, 
     }
 }
 
-// Producer kernel: grid (pair tiles, points), kSharedThreads threads, dynamic shared memory.
-__global__ void __launch_bounds__(kSharedThreads, 2) kernels_shared_kernel(acro_batch_t b, double* __restrict__ Kws, acro_params_t p) {
+// The kernel builder of the production path: grid (pair tiles, points), kSharedThreads threads, dynamic shared memory.
+// One thread owns one (E,E') pair of one model point and produces the five kernel planes for ALL temperatures of the
+// point: closed forms (pair-only parts computed once) and the temperature-shared integrals.  The (pair, T) combinations
+// whose lower limit sits on the Wien tail are completed by kernels_wien_kernel (below).
+__global__ void __launch_bounds__(kSharedThreads, 2) kernels_shared_kernel(acro_batch_t b, double* __restrict__ Kws, DeviceTables tb,
+                                                                          acro_params_t p) {
     extern __shared__ double sm[];
     const int pt = blockIdx.y;
     const int ne = b.pt_ne[pt], nt = b.pt_nt[pt], s0 = b.pt_sys_off[pt];
@@ -244,6 +255,7 @@ __global__ void __launch_bounds__(kSharedThreads, 2) kernels_shared_kernel(acro_
     double* six = sx + kMaxPan * kPanN;
     double* sy = six + kMaxPan * kPanN;
     double* sB = sy + kMaxPan * kPanN;                 // [nn][kTT]
+    double* sT = sB + (size_t)kMaxPan * kPanN * kTT;   // per-temperature scalars of the tile: T, ne, nNZ2, photon-photon prefactor
     for (int k = threadIdx.x; k < nn; k += blockDim.x) {
         double lo, h;
         panel_geom(g, k / kPanN, lo, h);
@@ -275,14 +287,33 @@ __global__ void __launch_bounds__(kSharedThreads, 2) kernels_shared_kernel(acro_
     const PairLimits L = pair_limits(E, Ep);
     const double x_bot = exp(g.y_bot);
     const int64_t np = b.n_pairs_total;
+    // pair-only parts of the closed forms (cascade.py:383-402, 550-558, 621-639)
+    const double a2 = kAlpha * kAlpha;
+    const double pre_ic = 2.0 * kPi * a2 / (Ep * Ep);
+    const double pre_pc = 0.25 * kPi * a2 * kMe2 / (Ep * Ep * Ep);
+    const double rr = E / Ep, gg_shape = 1.0 - rr + rr * rr;
+    const double pp_pair = 1112.0 / (10125.0 * kPi) * (a2 * a2) / ((kMe2 * kMe2) * (kMe2 * kMe2)) * 8.0 * (kPi2 * kPi2) / 63.0 *
+                           (Ep * Ep) * (gg_shape * gg_shape);
+    const double compton_g = kernel_compton_core(E, Ep, 1.0);               // per unit electron density
+    const double compton_e = kernel_compton_core(Ep + kMe - E, Ep, 1.0);
+    const double bh_pair = (L.xa9 > 0.0) ? bh_dsdE_Z2(E, Ep) : 0.0;         // same condition E' >= E + me
+
     for (int t0 = 0; t0 < nt; t0 += kTT) {
+        __syncthreads();
+        if (threadIdx.x < kTT) {
+            const int t = threadIdx.x;
+            const double T = b.sys_T[s0 + min(t0 + t, nt - 1)];
+            const Densities d = densities(T, tb.eta, tb.Yp, tb.YHe4);
+            const double T3 = T * T * T;
+            sT[t] = T; sT[kTT + t] = d.ne; sT[2 * kTT + t] = d.nNZ2; sT[3 * kTT + t] = T3 * T3;
+        }
         __syncthreads();
         // Bose table of this temperature tile: raw x^2/(pi^2 (e^{x/T}-1)), zero above the cut-off 200 T
         for (int idx = threadIdx.x; idx < nn * kTT; idx += blockDim.x) {
             const int k = idx / kTT, t = idx % kTT;
             double v = 0.0;
             if (t0 + t < nt) {
-                const double T = b.sys_T[s0 + t0 + t];
+                const double T = sT[t];
                 const double x = sx[k];
                 if (x <= p.Ephb_T_max * T) v = x * x * bose_inv(x / T) * (1.0 / kPi2);
             }
@@ -290,36 +321,124 @@ __global__ void __launch_bounds__(kSharedThreads, 2) kernels_shared_kernel(acro_
         }
         __syncthreads();
         double acc[kTT];
-        // e -> gamma
+        const int ntile = min(kTT, nt - t0);
+        // a pair takes part in the shared integrals of this tile only if its lower limit is off the Wien tail for the
+        // tile's highest temperature
+        const double xa_max = kSteepX * sT[ntile - 1];
+        // ---- e -> gamma (plane 1)
         {
-            const bool act = active && L.xa9 > 0.0 && L.xb9 > L.xa9;
+            const bool has = active && L.xa9 > 0.0;
+            const bool act = has && L.xb9 > L.xa9 && L.xa9 <= xa_max;
             shared_integral<KIND_IC_PHOTON>(c, L.xa9, L.xb9, g, sx, six, sy, sB, act, acc);
-            if (act)
-                for (int t = 0; t < kTT && t0 + t < nt; ++t) {
-                    const double T = b.sys_T[s0 + t0 + t];
-                    if (shared_regime(L.xa9, L.xb9, T, p.Ephb_T_max, x_bot, Tmin)) Kws[1 * np + b.sys_k_off[s0 + t0 + t] + loc] = acc[t];
+            if (active)
+                for (int t = 0; t < ntile; ++t) {
+                    const double T = sT[t];
+                    double v = 0.0;
+                    if (has) {
+                        const double ulim = fmin(L.xb9, p.Ephb_T_max * T);
+                        if (ulim > L.xa9 && shared_regime(L.xa9, L.xb9, T, p.Ephb_T_max, x_bot, Tmin)) v = pre_ic * acc[t];
+                    }
+                    Kws[1 * np + b.sys_k_off[s0 + t0 + t] + loc] = v;
                 }
         }
-        // e -> e
+        // ---- e -> e (plane 4)
         {
-            const bool act = active && L.xa10 > 0.0 && L.xb10 > L.xa10;
+            const bool has = active && L.xa10 > 0.0;
+            const bool act = has && L.xb10 > L.xa10 && L.xa10 <= xa_max;
             shared_integral<KIND_IC_ELECTRON>(c, L.xa10, L.xb10, g, sx, six, sy, sB, act, acc);
-            if (act)
-                for (int t = 0; t < kTT && t0 + t < nt; ++t) {
-                    const double T = b.sys_T[s0 + t0 + t];
-                    if (shared_regime(L.xa10, L.xb10, T, p.Ephb_T_max, x_bot, Tmin)) Kws[4 * np + b.sys_k_off[s0 + t0 + t] + loc] = acc[t];
+            if (active)
+                for (int t = 0; t < ntile; ++t) {
+                    const double T = sT[t];
+                    double v = 0.0;
+                    if (has) {
+                        const double ulim = fmin(L.xb10, p.Ephb_T_max * T);
+                        if (ulim > L.xa10 && shared_regime(L.xa10, L.xb10, T, p.Ephb_T_max, x_bot, Tmin)) v = pre_ic * acc[t];
+                    }
+                    Kws[4 * np + b.sys_k_off[s0 + t0 + t] + loc] = v;
                 }
         }
-        // gamma -> e (pair creation): integrand G * x / (e^{x/T}-1) = (G/x) * x^2 / (...): the table holds x^2
+        // ---- gamma -> e-/e+ (planes 2, 3) and gamma -> gamma (plane 0)
         {
-            const bool act = active && L.xa11 > 0.0 && L.xb11 > L.xa11;
+            const bool has = active && L.xb11 > L.xa11;
+            const bool act = has && L.xa11 <= xa_max && !(Ep < kMe2 / (50.0 * sT[ntile - 1]));
             shared_integral<KIND_PC_ELECTRON>(c, L.xa11, L.xb11, g, sx, six, sy, sB, act, acc);
-            if (act)
-                for (int t = 0; t < kTT && t0 + t < nt; ++t) {
-                    const double T = b.sys_T[s0 + t0 + t];
-                    if (!(Ep < kMe2 / (50.0 * T)) && shared_regime(L.xa11, L.xb11, T, p.Ephb_T_max, x_bot, Tmin))
-                        Kws[3 * np + b.sys_k_off[s0 + t0 + t] + loc] = acc[t];
+            if (active)
+                for (int t = 0; t < ntile; ++t) {
+                    const double T = sT[t], dne = sT[kTT + t], dnz = sT[2 * kTT + t];
+                    double pair = dnz * bh_pair;
+                    if (has && !(Ep < kMe2 / (50.0 * T))) {
+                        const double ulim = fmin(L.xb11, p.Ephb_T_max * T);
+                        if (ulim > L.xa11 && shared_regime(L.xa11, L.xb11, T, p.Ephb_T_max, x_bot, Tmin)) pair += pre_pc * acc[t];
+                    }
+                    const int64_t o = b.sys_k_off[s0 + t0 + t] + loc;
+                    Kws[3 * np + o] = pair;
+                    Kws[2 * np + o] = pair + dne * compton_e;
+                    Kws[0 * np + o] = pp_pair * sT[3 * kTT + t] * exp(-Ep * T / kMe2) + dne * compton_g;
                 }
+        }
+    }
+}
+
+// Second kernel of the production path: one thread per (system, pair).  Only the (pair, T) combinations that the shared
+// grid does not serve (lower limit on the Wien tail) do any work here: their own Gauss-Laguerre / Gauss-Legendre rule
+// (acro_fastquad.cuh), written over / added to what kernels_shared_kernel left in the planes.
+#ifndef ACRO_WT_MINBLOCKS
+#define ACRO_WT_MINBLOCKS 6
+#endif
+template <int Q>
+__global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(acro_batch_t b, double* __restrict__ Kws, acro_params_t p) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= b.n_pairs_total) return;
+    // owner system by binary search on the plane offsets
+    int lo_s = 0, hi_s = b.n_systems - 1;
+    while (lo_s < hi_s) {
+        const int mid = (lo_s + hi_s + 1) >> 1;
+        if (b.sys_k_off[mid] <= tid) lo_s = mid; else hi_s = mid - 1;
+    }
+    const int s = lo_s;
+    const int64_t loc = tid - b.sys_k_off[s];
+    const int pt = b.sys_point[s];
+    const int ne = b.pt_ne[pt];
+    const double tn = 2.0 * ne + 1.0;
+    int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+    i = max(0, min(i, ne - 1));
+    while (i > 0 && tri_row_off(i, ne) > loc) --i;
+    while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
+    const int j = i + (int)(loc - tri_row_off(i, ne));
+    const double* eg = b.e_grid + b.pt_e_off[pt];
+    const double E = eg[i], Ep = eg[j], T = b.sys_T[s];
+    const int s0 = b.pt_sys_off[pt], nt = b.pt_nt[pt];
+    const double Tmin = b.sys_T[s0];
+    const SharedGrid g = shared_grid(Tmin, b.sys_T[s0 + nt - 1], eg[ne - 1], p.Ephb_T_max);
+    const double x_bot = exp(g.y_bot);
+    const PairLimits L = pair_limits(E, Ep);
+    const double xmax = p.Ephb_T_max * T;
+    const int64_t np = b.n_pairs_total;
+    const double a2 = kAlpha * kAlpha;
+    PairConst c;
+    c.E = E; c.Ep = Ep; c.dE = Ep - E;
+    if (L.xa9 > 0.0) {
+        const double ulim = fmin(L.xb9, xmax);
+        if (ulim > L.xa9 && !shared_regime(L.xa9, L.xb9, T, p.Ephb_T_max, x_bot, Tmin)) {
+            const double r = E / c.dE;
+            c.c9 = r * r / (2.0 + 2.0 * r);
+            Kws[1 * np + tid] = 2.0 * kPi * a2 / (Ep * Ep) * thermal_integral<KIND_IC_PHOTON, Q>(c, T, L.xa9, ulim);
+        }
+    }
+    if (L.xa10 > 0.0) {
+        const double ulim = fmin(L.xb10, xmax);
+        if (ulim > L.xa10 && !shared_regime(L.xa10, L.xb10, T, p.Ephb_T_max, x_bot, Tmin)) {
+            c.c10 = 0.25 * kMe2 / Ep;
+            c.i2Ep = 0.5 / Ep;
+            Kws[4 * np + tid] = 2.0 * kPi * a2 / (Ep * Ep) * thermal_integral<KIND_IC_ELECTRON, Q>(c, T, L.xa10, ulim);
+        }
+    }
+    if (L.xb11 > L.xa11 && !(Ep < kMe2 / (50.0 * T))) {
+        const double ulim = fmin(L.xb11, xmax);
+        if (ulim > L.xa11 && !shared_regime(L.xa11, L.xb11, T, p.Ephb_T_max, x_bot, Tmin)) {
+            const double add = 0.25 * kPi * a2 * kMe2 / (Ep * Ep * Ep) * thermal_integral<KIND_PC_ELECTRON, Q>(c, T, L.xa11, ulim);
+            Kws[3 * np + tid] += add;
+            Kws[2 * np + tid] += add;
         }
     }
 }
