@@ -102,6 +102,7 @@ class InputInterface(object):
         pd = input_data.get_param_data()
         self._sParamData = dict(pd.reshape(pd.size))
         self._sTempRange = None
+        self._sSearch = {}      # per column: (ascending copy for searchsorted, descending flag)
         self._check_data()
 
     def _check_data(self):
@@ -117,21 +118,27 @@ class InputInterface(object):
 
     # 1. COSMO_DATA ###########################################################
 
-    def _bracket(self, x, v):
+    def _bracket(self, x, v, xc=None):
         """Index ix with v between x[ix] and x[ix+1]; x monotone (either direction); v scalar or array."""
         n = x.shape[0]
-        if x[0] < x[1]:
-            ix = np.searchsorted(x, v, side="right") - 1
-        else:
-            ix = n - np.searchsorted(x[::-1], v, side="left") - 1
-        return ix
+        key = xc
+        ent = self._sSearch.get(key) if key is not None else None
+        if ent is None:
+            asc = bool(x[0] < x[1])
+            ent = (np.ascontiguousarray(x if asc else x[::-1]), asc)
+            if key is not None:
+                self._sSearch[key] = ent
+        xs, asc = ent
+        if asc:
+            return np.searchsorted(xs, v, side="right") - 1
+        return n - np.searchsorted(xs, v, side="left") - 1
 
     def _interp_cosmo_data(self, val, xc, yc):
         x = self._sCosmoDataLog[:, xc]
         y = self._sCosmoDataLog[:, yc]
         if np.ndim(val) == 0:
             val_log = log10(val)
-            ix = int(self._bracket(x, val_log))
+            ix = int(self._bracket(x, val_log, xc))
             n = x.shape[0]
             if ix < 0 or ix > n - 2 or not (x[ix] <= val_log <= x[ix + 1] or x[ix] >= val_log >= x[ix + 1]):
                 raise ValueError("Interpolation error: Index out of range")
@@ -139,9 +146,9 @@ class InputInterface(object):
             b = y[ix] - m * x[ix]
             return 10.**(m * val_log + b)
         val_log = np.log10(np.asarray(val, dtype=np.float64))
-        ix = self._bracket(x, val_log)
+        ix = self._bracket(x, val_log, xc)
         n = x.shape[0]
-        if np.any(ix < 0) or np.any(ix > n - 2):
+        if ix.size and (ix.min() < 0 or ix.max() > n - 2):
             raise ValueError("Interpolation error: Index out of range")
         m = (y[ix + 1] - y[ix]) / (x[ix + 1] - x[ix])
         b = y[ix] - m * x[ix]

@@ -99,6 +99,12 @@ class AbstractModel(ABC):
         S0, mode, sc, sc_E = self._source_arrays(T, E_grid)
         return PointSpec(self._sE0, E_grid, T, S0, self._t_at_tmax(), mode, sc, sc_E)
 
+    @classmethod
+    def point_specs(cls, models):
+        """PointSpecs of many models of this class.  Built-in models vectorise the source arrays over the whole group
+        (one table interpolation for all temperatures of all models); the default is one by one."""
+        return [m.point_spec() for m in models]
+
     def _pdi_matrix(self):
         eng = self._engine()
         if self._sMatpBuffer is None:
@@ -221,6 +227,40 @@ class DecayModel(AbstractModel):
         sc = np.column_stack([self._sBRee * nd, np.zeros_like(nd), np.zeros_like(nd)])
         sc_E = np.column_stack([_fsr_shape(E_grid, self._sE0), np.zeros(len(E_grid)), np.zeros(len(E_grid))])
         return S0, _lib.SC_SEPARABLE, sc, sc_E
+
+
+    @classmethod
+    def point_specs(cls, models):
+        if not models or any(type(m) is not DecayModel for m in models) or len({id(m._sII) for m in models}) != 1:
+            return [m.point_spec() for m in models]
+        ii = models[0]._sII
+        Ts = [temperature_grid(*m._sTrg) for m in models]
+        nt = np.array([len(t) for t in Ts])
+        Tall = np.concatenate(Ts)
+        rep = lambda vals: np.repeat(np.array(vals, dtype=np.float64), nt)
+        sf0 = rep([ii.scale_factor(m._sT0) for m in models]) if len({m._sT0 for m in models}) > 1 else \
+            float(ii.scale_factor(models[0]._sT0))
+        sf_ratio = sf0 / ii.scale_factor(Tall)
+        delta_t = ii.time(Tall) - rep([m._st0 for m in models])
+        n_gamma = (2. * zeta3) * (rep([m._sT0 for m in models])**3.) / (pi**2.)
+        tau = rep([m._sTau for m in models])
+        nd_all = rep([m._sN0a for m in models]) * n_gamma * sf_ratio**3. * np.exp(-delta_t / tau) * (hbar / tau)
+        t_tmax = ii.time(np.array([max(m._sTrg) for m in models]))
+        specs, off = [], 0
+        for k, m in enumerate(models):
+            nd = nd_all[off:off + nt[k]]
+            off += nt[k]
+            E_grid = energy_grid(m._sE0)
+            S0 = np.column_stack([m._sBRaa * 2. * nd, m._sBRee * nd, m._sBRee * nd])
+            if m._sBRee == 0.:
+                specs.append(PointSpec(m._sE0, E_grid, Ts[k], S0, t_tmax[k]))
+            else:
+                z = np.zeros_like(nd)
+                sc = np.column_stack([m._sBRee * nd, z, z])
+                ze = np.zeros(len(E_grid))
+                sc_E = np.column_stack([_fsr_shape(E_grid, m._sE0), ze, ze])
+                specs.append(PointSpec(m._sE0, E_grid, Ts[k], S0, t_tmax[k], _lib.SC_SEPARABLE, sc, sc_E))
+        return specs
 
 
 class AnnihilationModel(AbstractModel):

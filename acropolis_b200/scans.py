@@ -120,7 +120,8 @@ def run_models(models, devices=None, want_matp=False):
             work.append(i)
     if not work:
         return (Yf, matp) if want_matp else Yf
-    specs = [models[i].point_spec() for i in work]
+    wm = [models[i] for i in work]
+    specs = type(wm[0]).point_specs(wm) if len({type(m) for m in wm}) == 1 else [m.point_spec() for m in wm]
     import torch
     if devices is None:
         dist = _dist_world()
@@ -173,7 +174,7 @@ def run_points(model, param_sets, devices=None, group=256):
 
     ncol = 3
     for g0 in range(0, N, group):
-        idx, specs = [], []
+        idx, todo = [], []
         for i in range(g0, min(g0 + group, N)):
             m = model(**param_sets[i])
             ncol = m._sII.bbn_abundances().shape[1]
@@ -186,8 +187,9 @@ def run_points(model, param_sets, devices=None, group=256):
                     eng = Engine.get(m._sII, devices[0])
                     eng.last_h2d_bytes = eng.last_d2h_bytes = 0
                 idx.append(i)
-                specs.append(m.point_spec())
-        if specs:
+                todo.append(m)
+        if todo:
+            specs = type(todo[0]).point_specs(todo) if len({type(m) for m in todo}) == 1 else [m.point_spec() for m in todo]
             in_flight.append((idx, eng.submit(specs, want=("Yf", "status"))))
         while len(in_flight) > 2:
             finish(in_flight.pop(0))
