@@ -24,10 +24,11 @@
 
 namespace acro {
 
-// Gauss-Laguerre rules n = 12, 16, 24 packed back to back (offsets 0, 12, 28): nodes, weights (include e^{-s}), e^{-s_k}
-__constant__ double c_lag_s[52];
-__constant__ double c_lag_w[52];
-__constant__ double c_lag_es[52];
+// Gauss-Laguerre rules n = 4, 6, 8, 12, 16, 24 packed back to back (offsets 0, 4, 10, 18, 30, 46): nodes, weights
+// (include e^{-s}), e^{-s_k}
+__constant__ double c_lag_s[70];
+__constant__ double c_lag_w[70];
+__constant__ double c_lag_es[70];
 
 __constant__ double c_half_range = 8.0;           // log-range [e-folds] up to which Q/2 nodes are used (a9, a11 only)
 constexpr double kSteepX = 2.718281828459045;   // x_a/T above which the Laguerre form is used (u_a > 1)
@@ -144,10 +145,16 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
     const double va = x_a * iT;
     if (va > kSteepX && (x_b - x_a) * iT >= kSteepSpan) {
         // Gauss-Laguerre in s = (x - x_a)/T.  The further out on the Wien tail, the smoother the integrand on the scale of
-        // the weight: 24 nodes for e < x_a/T <= e^1.5, 16 up to e^2, 12 beyond (prototype: <= 6e-11 in each band).
+        // the weight, so the order follows va = x_a/T (worst relative error of each band in tools/proto, all <= 4e-10):
+        //   va in (e, e^1.5]: 24   (e^1.5, e^2]: 16   (e^2, e^2.5]: 12   (e^2.5, e^3]: 8   (e^3, e^4]: 6   > e^4: 4
         const double Ea = fexp(-va);
-        const int n = (va > 7.38905609893065) ? 12 : ((va > 4.4816890703380645) ? 16 : 24);
-        const int off = (n == 12) ? 0 : ((n == 16) ? 12 : 28);
+        int n, off;
+        if (va > 54.598150033144236) { n = 4; off = 0; }
+        else if (va > 20.085536923187668) { n = 6; off = 4; }
+        else if (va > 12.182493960703473) { n = 8; off = 10; }
+        else if (va > 7.38905609893065) { n = 12; off = 18; }
+        else if (va > 4.4816890703380645) { n = 16; off = 30; }
+        else { n = 24; off = 46; }
         double sum = 0.0;
 #pragma unroll 1
         for (int kk = 0; kk < n; ++kk) {

@@ -93,11 +93,13 @@ cudaError_t upload_quadrature_tables() {
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_glw, w.data(), sizeof(double) * kGLTotal);
     if (e != cudaSuccess) return e;
-    double ls[52], lw[52], les[52];
-    gauss_laguerre(12, ls, lw);
-    gauss_laguerre(16, ls + 12, lw + 12);
-    gauss_laguerre(24, ls + 28, lw + 28);
-    for (int i = 0; i < 52; ++i) les[i] = std::exp(-ls[i]);
+    double ls[70], lw[70], les[70];
+    {
+        const int orders_l[6] = {4, 6, 8, 12, 16, 24};
+        int off = 0;
+        for (int o : orders_l) { gauss_laguerre(o, ls + off, lw + off); off += o; }
+    }
+    for (int i = 0; i < 70; ++i) les[i] = std::exp(-ls[i]);
     if ((e = cudaMemcpyToSymbol(c_lag_s, ls, sizeof(ls))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_lag_w, lw, sizeof(lw))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_lag_es, les, sizeof(les))) != cudaSuccess) return e;

@@ -281,6 +281,11 @@ def main_gpu(args):
     hbm_peak_src = "MEASURED_PEAKS.json" if hbm_peak else "fallback (B200_PROFILING.md)"
     hbm_peak = hbm_peak or 6650.0
     solve_bytes = 5 * 8 * pairs       # the solve stage reads every K entry once (G, F, S0 are <1% of that)
+    # DRAM traffic and executed-FP64 utilisation of the two kernel-builder kernels from the committed ncu captures of one
+    # slice (profiles/r01_ncu_kernels_shared_kernel.txt, r01_ncu_kernels_wien_kernel.txt): bytes per slice, i.e. per launch pair
+    ncu = {"traffic_bytes_per_launch": 28.43e9 + 11.02e9, "algorithmic_bytes_per_launch": 5 * 8 * pairs / max(k_launches, 1),
+           "fp64_pipe_active_pct": {"kernels_shared_kernel": 38.4, "kernels_wien_kernel": 62.5},
+           "source": "profiles/r01_ncu_kernels_shared_kernel.txt, profiles/r01_ncu_kernels_wien_kernel.txt"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config({"chunks_per_step": len(staged[-1])}),
@@ -288,13 +293,17 @@ def main_gpu(args):
                     "api": "acropolis_b200.scans.run_points (model construction + source arrays + pinned H2D + kernels + D2H)",
                     "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": int(dev_launches), "gpu_launches_total_all_arms": int(total_launches),
-            "roofline": {"kernel": "kernels_kernel<64> (K-plane builder, stage i)", "bound": "fp64", "achieved": achieved,
-                         "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+            "roofline": {"kernel": "kernel builder, stage (i): kernels_shared_kernel + kernels_wien_kernel<%d>" % prm.quad_order,
+                         "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         "traffic": ncu["traffic_bytes_per_launch"],
                          "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "note": "achieved = ALGORITHMIC flop (SURVEY 8d: Q=63 nodes per (E,E',T) integral) / measured stage time; it "
+                                 "can exceed the DFMA peak because F/G are evaluated once per (E,E',node) for all temperatures of a "
+                                 "point and the Wien tail uses 4-24 Gauss-Laguerre nodes; executed-FP64 utilisation is in `ncu`",
                          "algorithmic_flop_per_launch": flop_kernels / max(k_launches, 1),
                          "avg_launch_ms": stage_ms[1] / max(k_launches, 1),
                          "census": {"pairs": pairs, "N_a9": n9, "N_a10": n10, "N_a11": n11, "Q": Q},
-                         "share_of_step": stage_ms[1] / stage_ms.sum()},
+                         "share_of_step": stage_ms[1] / stage_ms.sum(), "ncu": ncu},
             "roofline_solve": {"kernel": "solve_pdi_kernel (stage ii+iii)", "bound": "hbm", "achieved": solve_bytes / (stage_ms[2] * 1e-3) / 1e9,
                                "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / (stage_ms[2] * 1e-3) / 1e9 / hbm_peak,
                                "peak_source": hbm_peak_src, "traffic": None},
