@@ -172,3 +172,43 @@ def test_reference_convergence_rows(gpu_engine):
     # the stored rows have 6 significant digits; the reference's own quadrature noise on Y_D is ~1e-5 relative
     err = np.abs(Y_D / refs - 1)
     assert np.max(err) < 1e-4 and np.median(err) < 1e-5
+
+
+def test_high_resolution_point_vs_oracle(gpu_engine):
+    """BASELINE config 5 flavour: cfg1 at 2x the default resolution (NE_pd=240, NT_pd=40 -> NE=125, NT=80: four
+    temperature tiles in the shared-grid kernel), against the oracle at the same resolution."""
+    import acropolis_b200.params as params
+    from acropolis_b200.models import DecayModel
+    from oracle_helpers import get_oracle
+    old = (params.NE_pd, params.NT_pd)
+    try:
+        params.NE_pd, params.NT_pd = 240, 40
+        sp = DecayModel(10., 1e5, 10., 1e-10, 0., 1.).point_spec()
+    finally:
+        params.NE_pd, params.NT_pd = old
+    assert len(sp.E_grid) == 125 and len(sp.T) in (79, 80)
+    out = gpu_engine.run([sp], want=("F", "pdi", "Yf"))
+    ref = get_oracle(1e-3).run_point(sp)
+    F = out["F"].reshape(len(sp.T), 3, len(sp.E_grid))
+    assert relerr(F, ref["F"]) < 1e-5
+    assert relerr(out["pdi"], ref["pdi"], 1e-100) < 1.5e-3
+    assert relerr(out["Yf"][0], ref["Yf"], 1e-30) < 1e-4
+
+
+def test_kernel_modes_agree_on_abundances(gpu_engine):
+    """The three evaluations of the thermal kernel integrals (production, per-(pair,T), plain Gauss-Legendre) give the
+    same spectra and abundances for a ragged batch."""
+    import acropolis_b200.params as params
+    from oracle_helpers import spec_from_golden
+    specs = [spec_from_golden(golden(n + ".npz")) for n in ("decay_nemin", "cfg1_decay", "decay_ee", "decay_highT", "cfg2_annih")]
+    res = {}
+    try:
+        for mode in (0, 1, 2):
+            params.kernel_mode = mode
+            res[mode] = gpu_engine.run(specs, want=("F", "Yf"))
+    finally:
+        params.kernel_mode = 0
+    for mode in (1, 2):
+        live = res[0]["F"] > 1e-150
+        assert np.max(np.abs(res[mode]["F"][live] / res[0]["F"][live] - 1)) < 1e-7
+        assert relerr(res[mode]["Yf"], res[0]["Yf"], 1e-30) < 1e-8
