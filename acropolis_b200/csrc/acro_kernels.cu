@@ -1181,11 +1181,12 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
             kernels_shared_kernel<<<grid, kSharedThreads, smem, st>>>(b, Kws, t, p);
             lc.launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            dim3 gw((unsigned)((tri_max + 127) / 128), (unsigned)b.n_points);
             switch (p.quad_order) {
-                case 16: kernels_wien_kernel<16><<<g, 128, 0, st>>>(b, Kws, p); break;
-                case 32: kernels_wien_kernel<32><<<g, 128, 0, st>>>(b, Kws, p); break;
-                case 96: kernels_wien_kernel<96><<<g, 128, 0, st>>>(b, Kws, p); break;
-                default: kernels_wien_kernel<64><<<g, 128, 0, st>>>(b, Kws, p); break;
+                case 16: kernels_wien_kernel<16><<<gw, 128, 0, st>>>(b, Kws, p); break;
+                case 32: kernels_wien_kernel<32><<<gw, 128, 0, st>>>(b, Kws, p); break;
+                case 96: kernels_wien_kernel<96><<<gw, 128, 0, st>>>(b, Kws, p); break;
+                default: kernels_wien_kernel<64><<<gw, 128, 0, st>>>(b, Kws, p); break;
             }
             if (e != cudaSuccess) return e;
             lc.launches++;

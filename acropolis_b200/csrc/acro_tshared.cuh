@@ -379,26 +379,20 @@ __global__ void __launch_bounds__(kSharedThreads, 2) kernels_shared_kernel(acro_
     }
 }
 
-// Second kernel of the production path: one thread per (system, pair).  Only the (pair, T) combinations that the shared
-// grid does not serve (lower limit on the Wien tail) do any work here: their own Gauss-Laguerre / Gauss-Legendre rule
+// Second kernel of the production path: one thread per (point, pair), looping over the temperatures of the point (the
+// index decode, limits and grid are per pair, not per (pair,T)).  Only the (pair, T) combinations that the shared grid
+// does not serve (lower limit on the Wien tail) do any work: their own Gauss-Laguerre / Gauss-Legendre rule
 // (acro_fastquad.cuh), written over / added to what kernels_shared_kernel left in the planes.
 #ifndef ACRO_WT_MINBLOCKS
 #define ACRO_WT_MINBLOCKS 6
 #endif
 template <int Q>
 __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(acro_batch_t b, double* __restrict__ Kws, acro_params_t p) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= b.n_pairs_total) return;
-    // owner system by binary search on the plane offsets
-    int lo_s = 0, hi_s = b.n_systems - 1;
-    while (lo_s < hi_s) {
-        const int mid = (lo_s + hi_s + 1) >> 1;
-        if (b.sys_k_off[mid] <= tid) lo_s = mid; else hi_s = mid - 1;
-    }
-    const int s = lo_s;
-    const int64_t loc = tid - b.sys_k_off[s];
-    const int pt = b.sys_point[s];
-    const int ne = b.pt_ne[pt];
+    const int pt = blockIdx.y;
+    const int ne = b.pt_ne[pt], nt = b.pt_nt[pt], s0 = b.pt_sys_off[pt];
+    const int64_t tri = (int64_t)ne * (ne + 1) / 2;
+    const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc >= tri) return;
     const double tn = 2.0 * ne + 1.0;
     int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
     i = max(0, min(i, ne - 1));
@@ -406,39 +400,48 @@ __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(ac
     while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
     const int j = i + (int)(loc - tri_row_off(i, ne));
     const double* eg = b.e_grid + b.pt_e_off[pt];
-    const double E = eg[i], Ep = eg[j], T = b.sys_T[s];
-    const int s0 = b.pt_sys_off[pt], nt = b.pt_nt[pt];
-    const double Tmin = b.sys_T[s0];
-    const SharedGrid g = shared_grid(Tmin, b.sys_T[s0 + nt - 1], eg[ne - 1], p.Ephb_T_max);
-    const double x_bot = exp(g.y_bot);
+    const double E = eg[i], Ep = eg[j];
+    const double Tmin = b.sys_T[s0], Tmax = b.sys_T[s0 + nt - 1];
     const PairLimits L = pair_limits(E, Ep);
-    const double xmax = p.Ephb_T_max * T;
+    // nothing to do for this pair if every lower limit is off the Wien tail even at the lowest temperature
+    const double xa_lo = fmin(fmin(L.xa9 > 0.0 ? L.xa9 : 1e300, L.xa10 > 0.0 ? L.xa10 : 1e300), L.xb11 > L.xa11 ? L.xa11 : 1e300);
+    const SharedGrid g = shared_grid(Tmin, Tmax, eg[ne - 1], p.Ephb_T_max);
+    const double x_bot = exp(g.y_bot);
+    const bool covered = (x_bot <= 2e-11 * Tmin);
+    if (xa_lo > 1e299 || (covered && fmax(fmax(L.xa9, L.xa10), L.xb11 > L.xa11 ? L.xa11 : -1.0) <= kSteepX * Tmin)) return;
     const int64_t np = b.n_pairs_total;
     const double a2 = kAlpha * kAlpha;
+    const double pre_ic = 2.0 * kPi * a2 / (Ep * Ep), pre_pc = 0.25 * kPi * a2 * kMe2 / (Ep * Ep * Ep);
     PairConst c;
     c.E = E; c.Ep = Ep; c.dE = Ep - E;
-    if (L.xa9 > 0.0) {
-        const double ulim = fmin(L.xb9, xmax);
-        if (ulim > L.xa9 && !shared_regime(L.xa9, L.xb9, T, p.Ephb_T_max, x_bot, Tmin)) {
-            const double r = E / c.dE;
-            c.c9 = r * r / (2.0 + 2.0 * r);
-            Kws[1 * np + tid] = 2.0 * kPi * a2 / (Ep * Ep) * thermal_integral<KIND_IC_PHOTON, Q>(c, T, L.xa9, ulim);
-        }
+    {
+        const double r = E / fmax(c.dE, 1e-300);
+        c.c9 = r * r / (2.0 + 2.0 * r);
+        c.c10 = 0.25 * kMe2 / Ep;
+        c.i2Ep = 0.5 / Ep;
     }
-    if (L.xa10 > 0.0) {
-        const double ulim = fmin(L.xb10, xmax);
-        if (ulim > L.xa10 && !shared_regime(L.xa10, L.xb10, T, p.Ephb_T_max, x_bot, Tmin)) {
-            c.c10 = 0.25 * kMe2 / Ep;
-            c.i2Ep = 0.5 / Ep;
-            Kws[4 * np + tid] = 2.0 * kPi * a2 / (Ep * Ep) * thermal_integral<KIND_IC_ELECTRON, Q>(c, T, L.xa10, ulim);
+    for (int t = 0; t < nt; ++t) {
+        const double T = b.sys_T[s0 + t];
+        // temperatures ascend: once all three lower limits are off the Wien tail, so they are for the rest of the grid
+        const double xmax = p.Ephb_T_max * T;
+        const int64_t o = b.sys_k_off[s0 + t] + loc;
+        if (L.xa9 > 0.0) {
+            const double ulim = fmin(L.xb9, xmax);
+            if (ulim > L.xa9 && !shared_regime(L.xa9, L.xb9, T, p.Ephb_T_max, x_bot, Tmin))
+                Kws[1 * np + o] = pre_ic * thermal_integral<KIND_IC_PHOTON, Q>(c, T, L.xa9, ulim);
         }
-    }
-    if (L.xb11 > L.xa11 && !(Ep < kMe2 / (50.0 * T))) {
-        const double ulim = fmin(L.xb11, xmax);
-        if (ulim > L.xa11 && !shared_regime(L.xa11, L.xb11, T, p.Ephb_T_max, x_bot, Tmin)) {
-            const double add = 0.25 * kPi * a2 * kMe2 / (Ep * Ep * Ep) * thermal_integral<KIND_PC_ELECTRON, Q>(c, T, L.xa11, ulim);
-            Kws[3 * np + tid] += add;
-            Kws[2 * np + tid] += add;
+        if (L.xa10 > 0.0) {
+            const double ulim = fmin(L.xb10, xmax);
+            if (ulim > L.xa10 && !shared_regime(L.xa10, L.xb10, T, p.Ephb_T_max, x_bot, Tmin))
+                Kws[4 * np + o] = pre_ic * thermal_integral<KIND_IC_ELECTRON, Q>(c, T, L.xa10, ulim);
+        }
+        if (L.xb11 > L.xa11 && !(Ep < kMe2 / (50.0 * T))) {
+            const double ulim = fmin(L.xb11, xmax);
+            if (ulim > L.xa11 && !shared_regime(L.xa11, L.xb11, T, p.Ephb_T_max, x_bot, Tmin)) {
+                const double add = pre_pc * thermal_integral<KIND_PC_ELECTRON, Q>(c, T, L.xa11, ulim);
+                Kws[3 * np + o] += add;
+                Kws[2 * np + o] += add;
+            }
         }
     }
 }
