@@ -29,10 +29,19 @@ namespace acro {
 #ifndef ACRO_TS_HC
 #define ACRO_TS_HC 2.0
 #endif
-constexpr int kTT = 20;         // temperatures per tile (accumulators per thread)
+#ifndef ACRO_TS_TT
+#define ACRO_TS_TT 20
+#endif
+#ifndef ACRO_TS_MAXPAN
+#define ACRO_TS_MAXPAN 28
+#endif
+#ifndef ACRO_TS_CTAS
+#define ACRO_TS_CTAS 2
+#endif
+constexpr int kTT = ACRO_TS_TT;         // temperatures per tile (accumulators per thread)
 constexpr double kHC = ACRO_TS_HC;   // width of the coarse panels [e-folds]
 constexpr int kPanN = 16;       // Gauss-Legendre nodes per panel
-constexpr int kMaxPan = 28;     // panels per point (12 fine + 12 coarse for a 2-decade T range; 17 + 11 for 4 decades)
+constexpr int kMaxPan = ACRO_TS_MAXPAN;     // panels per point (12 fine + 12 coarse for a 2-decade T range; 17 + 11 for 4 decades)
 constexpr int kSharedThreads = 256;
 
 __constant__ double c_leg_modal[kPanN][kPanN];   // (2j+1)/2 * w_m * P_j(x_m): Legendre coefficients from nodal values
@@ -239,7 +248,7 @@ __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, 
 // One thread owns one (E,E') pair of one model point and produces the five kernel planes for ALL temperatures of the
 // point: closed forms (pair-only parts computed once) and the temperature-shared integrals.  The (pair, T) combinations
 // whose lower limit sits on the Wien tail are completed by kernels_wien_kernel (below).
-__global__ void __launch_bounds__(kSharedThreads, 2) kernels_shared_kernel(acro_batch_t b, double* __restrict__ Kws, DeviceTables tb,
+__global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_kernel(acro_batch_t b, double* __restrict__ Kws, DeviceTables tb,
                                                                           acro_params_t p) {
     extern __shared__ double sm[];
     const int pt = blockIdx.y;
