@@ -212,3 +212,28 @@ def test_kernel_modes_agree_on_abundances(gpu_engine):
         live = res[0]["F"] > 1e-150
         assert np.max(np.abs(res[mode]["F"][live] / res[0]["F"][live] - 1)) < 1e-7
         assert relerr(res[mode]["Yf"], res[0]["Yf"], 1e-30) < 1e-8
+
+
+def test_edge_cases(gpu_engine):
+    """Empty input, all-trivial scan, a point just above Emin (NE_min grid), and an injection energy above 1 GeV
+    (status bit instead of the reference's printed warning, models.py:47-51)."""
+    from acropolis_b200 import _lib
+    from acropolis_b200.models import DecayModel
+    from acropolis_b200.scans import BufferedScanner, ScanParameter, run_points, run_models
+    assert run_models([]).shape == (0, 9, 3)
+    assert gpu_engine.run([], want=("Yf",))["Yf"].size == 0
+    rows = BufferedScanner(DecayModel, mphi=ScanParameter(0, 0.4, 3), tau=ScanParameter(4, 6, 2), temp0=10., n0a=1e-10,
+                           bree=0., braa=1.).perform_scan()
+    Y0 = DecayModel(1., 1e5, 10., 1e-10, 0., 1.).run_disintegration()
+    assert rows.shape == (6, 29) and np.array_equal(rows[:, 2:], np.tile(Y0.T.reshape(-1), (6, 1)))
+    m = DecayModel(3.0002, 1e6, 10., 1e-8, 0., 1.)          # E0 = 1.5001 MeV: NE = NE_min = 10 over a 7e-5 wide range
+    sp = m.point_spec()
+    assert len(sp.E_grid) == 10
+    out = gpu_engine.run([sp], want=("Yf", "F", "status"))
+    assert np.all(np.isfinite(out["Yf"])) and out["status"][0] == 0
+    big = DecayModel(2600., 1e6, 10., 1e-12, 0., 1.)        # E0 = 1.3 GeV: top of the grid leaves rates.db
+    out = gpu_engine.run([big.point_spec()], want=("Yf", "status"))
+    assert out["status"][0] & _lib.ST_E0_ABOVE_GEV and out["status"][0] & _lib.ST_DIRECT_RATE
+    assert np.all(np.isfinite(out["Yf"]))
+    r = run_points(DecayModel, [dict(mphi=20., tau=1e6, temp0=10., n0a=1e-9, bree=0., braa=1.)], group=1)
+    assert r.shape == (1, 6 + 27)
