@@ -659,9 +659,11 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
     const double* E = b.e_grid + b.pt_e_off[pt];
     const double T = b.sys_T[s];
     const double* g = G + b.sys_f_off[s] * 3;
-    double* wF  = smem + (size_t)wib * smem_stride;   // [3][ne]
-    double* lnF = wF + 3 * (size_t)ne;                // [ne]  log of the floored photon spectrum
-    double* lnE = lnF + ne;                           // [ne]
+    // per-warp shared memory: lnF[ne] | wF[3][ne] during the back-substitution; afterwards the wF region is reused for
+    // lnE[ne] and the 17x32 rate accumulators (stride = ne_max + max(3 ne_max, ne_max + 17*32))
+    double* lnF = smem + (size_t)wib * smem_stride;   // [ne]  log of the floored photon spectrum
+    double* wF  = lnF + ne;                           // [3][ne]
+    double* lnE = wF;                                 // [ne]   (after the solve)
     const int64_t np = b.n_pairs_total;
     const double* K0 = Kws + b.sys_k_off[s];
     const double S0[3] = {b.s0[(int64_t)s * 3], b.s0[(int64_t)s * 3 + 1], b.s0[(int64_t)s * 3 + 2]};
@@ -691,7 +693,6 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
             }
         }
     }
-    for (int i = lane; i < ne; i += 32) lnE[i] = log(E[i]);
     __syncwarp();
 
     // --- rows NE-2 .. 0 (cascade.py:201-224)
@@ -728,6 +729,8 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
         __syncwarp();
     }
     if (!pdi) return;
+    for (int i = lane; i < ne; i += 32) lnE[i] = log(E[i]);     // wF is dead from here on
+    __syncwarp();
 
     // --- photodisintegration rates (nucl.py:398-467)
     const double E0 = b.pt_e0[pt];
@@ -1216,7 +1219,7 @@ cudaError_t launch_solve_pdi(const acro_batch_t& b, const acro_out_t& o, const D
                              const double* Kws, cudaStream_t st, LaunchCounters& lc) {
     (void)t;
     if (b.n_systems == 0) return cudaSuccess;
-    const int stride = 5 * b.ne_max + ACRO_NR * 32;            // doubles per warp: wF[3][ne], lnF, lnE, pdi accumulators
+    const int stride = b.ne_max + max(3 * b.ne_max, b.ne_max + ACRO_NR * 32);   // doubles per warp, see the kernel
     int wpb = 4;
     while (wpb > 1 && (size_t)wpb * stride * sizeof(double) > 200 * 1024) wpb >>= 1;
     const size_t smem = (size_t)wpb * stride * sizeof(double);
