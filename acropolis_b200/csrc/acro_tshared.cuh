@@ -45,7 +45,10 @@ constexpr int kTT = ACRO_TS_TT;         // temperatures per tile (accumulators p
 constexpr double kHC = ACRO_TS_HC;   // width of the coarse panels [e-folds]
 constexpr int kPanN = 16;       // Gauss-Legendre nodes per panel
 constexpr int kMaxPan = ACRO_TS_MAXPAN;     // panels per point (12 fine + 12 coarse for a 2-decade T range; 17 + 11 for 4 decades)
-constexpr int kSharedThreads = 256;
+#ifndef ACRO_TS_THREADS
+#define ACRO_TS_THREADS 256
+#endif
+constexpr int kSharedThreads = ACRO_TS_THREADS;
 
 __constant__ double c_leg_modal[kPanN][kPanN];   // (2j+1)/2 * w_m * P_j(x_m): Legendre coefficients from nodal values
 __constant__ double c_leg_rec[kPanN][2];         // recurrence P_{j+1} = a_j t P_j - b_j P_{j-1}: a_j = (2j+1)/(j+1), b_j = j/(j+1)
