@@ -394,70 +394,165 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
     }
 }
 
-// Second kernel of the production path: one thread per (point, pair), looping over the temperatures of the point (the
-// index decode, limits and grid are per pair, not per (pair,T)).  Only the (pair, T) combinations that the shared grid
-// does not serve (lower limit on the Wien tail) do any work: their own Gauss-Laguerre / Gauss-Legendre rule
-// (acro_fastquad.cuh), written over / added to what kernels_shared_kernel left in the planes.
+// Second kernel of the production path: the (pair, T) combinations that the shared grid does not serve (lower limit on
+// the Wien tail) get their own Gauss-Laguerre / Gauss-Legendre rule (acro_fastquad.cuh), written over / added to what
+// kernels_shared_kernel left in the planes.
+//
+// Work distribution: a thread owns one (E,E') pair of a point; for each of the three integrals the temperatures it has to
+// do form a contiguous index range (temperatures ascend, all predicates are monotone).  The ranges differ a lot between
+// the 32 pairs of a warp (ncu: 15.6 of 32 lanes active when every lane simply loops over its own range), so the warp
+// pools its items: exclusive prefix sum of the range lengths, then 32 items at a time, each lane fetching the constants
+// of the owning pair with shuffles.
 #ifndef ACRO_WT_MINBLOCKS
 #define ACRO_WT_MINBLOCKS 6
 #endif
+
+// first index t in [0, nt) with pred(T[t]) true, for a predicate that is false...false true...true along the grid
+template <class Pred>
+__device__ __forceinline__ int first_true(const double* __restrict__ T, int nt, Pred pred) {
+    int lo = 0, hi = nt;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pred(T[mid])) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+constexpr int kWienChunk = 64;   // temperatures pooled per pass
+
+// Items are enumerated TEMPERATURE-MAJOR: for one temperature the lanes that have work form (nearly) a contiguous set of
+// neighbouring pairs with similar x_a/T, hence the same Gauss-Laguerre order and coalesced stores; pooling consecutive
+// temperatures fills the lanes that would idle.  (Pair-major pooling was measured 25 % SLOWER than no pooling: every
+// batch of 32 items then spans the whole x_a/T range of a pair and runs at the largest node count.)
+//   smask[t]  = ballot of the lanes whose range contains temperature c_lo + t,  spref[t] = exclusive prefix of popc
+template <int KIND, int Q>
+__device__ __forceinline__ void wien_pooled(const acro_batch_t& b, double* __restrict__ Kws, const acro_params_t& p, int s0, int nt,
+                                            int t_lo, int n_mine, double x_a, double x_b0, double c0, double c1, double c2,
+                                            double c3, double pre, long long loc, int lane, unsigned* __restrict__ smask,
+                                            int* __restrict__ spref) {
+    const int64_t np = b.n_pairs_total;
+    const int t_hi = t_lo + n_mine;
+    int w_lo = n_mine > 0 ? t_lo : nt, w_hi = n_mine > 0 ? t_hi : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        w_lo = min(w_lo, __shfl_xor_sync(0xffffffffu, w_lo, o));
+        w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o));
+    }
+    for (int c_lo = w_lo; c_lo < w_hi; c_lo += kWienChunk) {
+        const int nc = min(kWienChunk, w_hi - c_lo);
+        // masks and their prefix (lane tt handles temperature c_lo+tt and c_lo+32+tt)
+        __syncwarp();
+        for (int tt = 0; tt < nc; ++tt) {
+            const int t = c_lo + tt;
+            const unsigned m = __ballot_sync(0xffffffffu, t >= t_lo && t < t_hi);
+            if (lane == 0) smask[tt] = m;
+        }
+        __syncwarp();
+        int cnt0 = (lane < nc) ? __popc(smask[lane]) : 0;
+        int cnt1 = (32 + lane < nc) ? __popc(smask[32 + lane]) : 0;
+        int inc0 = cnt0, inc1 = cnt1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v0 = __shfl_up_sync(0xffffffffu, inc0, o), v1 = __shfl_up_sync(0xffffffffu, inc1, o);
+            if (lane >= o) { inc0 += v0; inc1 += v1; }
+        }
+        const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+        const int total = tot0 + __shfl_sync(0xffffffffu, inc1, 31);
+        spref[lane] = inc0 - cnt0;
+        spref[32 + lane] = tot0 + inc1 - cnt1;
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+            const int q = base + lane;
+            const bool live = q < total;
+            int tt = 0, own = 0;
+            if (live) {
+                int lo = 0, hi = nc - 1;          // last temperature slot whose exclusive prefix is <= q and that is non-empty
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (spref[mid] <= q) lo = mid; else hi = mid - 1;
+                }
+                tt = lo;
+                own = __fns(smask[tt], 0, q - spref[tt] + 1);   // the (q - prefix + 1)-th set bit
+            }
+            const double o_xa = shfl_d(x_a, own), o_xb0 = shfl_d(x_b0, own), o_pre = shfl_d(pre, own);
+            const double o_c0 = shfl_d(c0, own), o_c1 = shfl_d(c1, own), o_c2 = shfl_d(c2, own), o_c3 = shfl_d(c3, own);
+            const long long o_loc = __shfl_sync(0xffffffffu, loc, own);
+            if (live) {
+                const int t = c_lo + tt;
+                const double T = b.sys_T[s0 + t];
+                const double ulim = fmin(o_xb0, p.Ephb_T_max * T);
+                PairConst c;
+                if (KIND == KIND_IC_PHOTON) { c.c9 = o_c0; }
+                else if (KIND == KIND_IC_ELECTRON) { c.E = o_c0; c.dE = o_c1; c.c10 = o_c2; c.i2Ep = o_c3; }
+                else { c.E = o_c0; c.Ep = o_c1; }
+                const double v = o_pre * thermal_integral<KIND, Q>(c, T, o_xa, ulim);
+                const int64_t o = b.sys_k_off[s0 + t] + o_loc;
+                if (KIND == KIND_IC_PHOTON) Kws[1 * np + o] = v;
+                else if (KIND == KIND_IC_ELECTRON) Kws[4 * np + o] = v;
+                else { Kws[3 * np + o] += v; Kws[2 * np + o] += v; }
+            }
+        }
+    }
+}
+
 template <int Q>
 __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(acro_batch_t b, double* __restrict__ Kws, acro_params_t p) {
     const int pt = blockIdx.y;
     const int ne = b.pt_ne[pt], nt = b.pt_nt[pt], s0 = b.pt_sys_off[pt];
     const int64_t tri = (int64_t)ne * (ne + 1) / 2;
+    __shared__ unsigned smask_all[4 * kWienChunk];
+    __shared__ int spref_all[4 * kWienChunk];
+    const int lane = threadIdx.x & 31;
+    unsigned* smask = smask_all + (threadIdx.x >> 5) * kWienChunk;
+    int* spref = spref_all + (threadIdx.x >> 5) * kWienChunk;
     const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (loc >= tri) return;
+    if (loc - lane >= tri) return;                     // whole warp beyond the point's pairs
+    const bool valid = loc < tri;
+    const int64_t locc = valid ? loc : tri - 1;
     const double tn = 2.0 * ne + 1.0;
-    int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+    int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)locc)));
     i = max(0, min(i, ne - 1));
-    while (i > 0 && tri_row_off(i, ne) > loc) --i;
-    while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
-    const int j = i + (int)(loc - tri_row_off(i, ne));
+    while (i > 0 && tri_row_off(i, ne) > locc) --i;
+    while (i < ne - 1 && tri_row_off(i + 1, ne) <= locc) ++i;
+    const int j = i + (int)(locc - tri_row_off(i, ne));
     const double* eg = b.e_grid + b.pt_e_off[pt];
     const double E = eg[i], Ep = eg[j];
-    const double Tmin = b.sys_T[s0], Tmax = b.sys_T[s0 + nt - 1];
+    const double* Tg = b.sys_T + s0;
+    const double Tmin = Tg[0], Tmax = Tg[nt - 1];
     const PairLimits L = pair_limits(E, Ep);
-    // nothing to do for this pair if every lower limit is off the Wien tail even at the lowest temperature
-    const double xa_lo = fmin(fmin(L.xa9 > 0.0 ? L.xa9 : 1e300, L.xa10 > 0.0 ? L.xa10 : 1e300), L.xb11 > L.xa11 ? L.xa11 : 1e300);
     const SharedGrid g = shared_grid(Tmin, Tmax, eg[ne - 1], p.Ephb_T_max);
     const double x_bot = exp(g.y_bot);
-    const bool covered = (x_bot <= 2e-11 * Tmin);
-    if (xa_lo > 1e299 || (covered && fmax(fmax(L.xa9, L.xa10), L.xb11 > L.xa11 ? L.xa11 : -1.0) <= kSteepX * Tmin)) return;
-    const int64_t np = b.n_pairs_total;
+    const bool grid_full = (x_bot <= 2e-11 * Tmin);    // same expression as in shared_regime
     const double a2 = kAlpha * kAlpha;
     const double pre_ic = 2.0 * kPi * a2 / (Ep * Ep), pre_pc = 0.25 * kPi * a2 * kMe2 / (Ep * Ep * Ep);
-    PairConst c;
-    c.E = E; c.Ep = Ep; c.dE = Ep - E;
-    {
-        const double r = E / fmax(c.dE, 1e-300);
-        c.c9 = r * r / (2.0 + 2.0 * r);
-        c.c10 = 0.25 * kMe2 / Ep;
-        c.i2Ep = 0.5 / Ep;
+    const double xf = p.Ephb_T_max;
+    // range of temperature indices that this pair has to do for one integral: [first non-empty range, first T that the
+    // shared grid serves) -- the predicates are the expressions used by kernels_shared_kernel, evaluated on the same T
+    auto range = [&](double x_a, double x_b0, bool has, int t_extra, int& t_lo, int& n) {
+        t_lo = 0; n = 0;
+        if (!valid || !has || !(x_b0 > x_a)) return;
+        const int t_ne = first_true(Tg, nt, [&](double T) { return fmin(x_b0, xf * T) > x_a; });
+        const bool served = (x_a >= x_bot) || grid_full;
+        const int t_cut = served ? first_true(Tg, nt, [&](double T) { return x_a <= kSteepX * T; }) : nt;
+        t_lo = max(t_ne, t_extra);
+        n = max(0, t_cut - t_lo);
+    };
+    int t_lo, n;
+    {   // e -> gamma
+        range(L.xa9, L.xb9, L.xa9 > 0.0, 0, t_lo, n);
+        const double r = E / fmax(Ep - E, 1e-300);
+        wien_pooled<KIND_IC_PHOTON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa9, L.xb9, r * r / (2.0 + 2.0 * r), 0.0, 0.0, 0.0, pre_ic, loc, lane, smask, spref);
     }
-    for (int t = 0; t < nt; ++t) {
-        const double T = b.sys_T[s0 + t];
-        // temperatures ascend: once all three lower limits are off the Wien tail, so they are for the rest of the grid
-        const double xmax = p.Ephb_T_max * T;
-        const int64_t o = b.sys_k_off[s0 + t] + loc;
-        if (L.xa9 > 0.0) {
-            const double ulim = fmin(L.xb9, xmax);
-            if (ulim > L.xa9 && !shared_regime(L.xa9, L.xb9, T, p.Ephb_T_max, x_bot, Tmin))
-                Kws[1 * np + o] = pre_ic * thermal_integral<KIND_IC_PHOTON, Q>(c, T, L.xa9, ulim);
-        }
-        if (L.xa10 > 0.0) {
-            const double ulim = fmin(L.xb10, xmax);
-            if (ulim > L.xa10 && !shared_regime(L.xa10, L.xb10, T, p.Ephb_T_max, x_bot, Tmin))
-                Kws[4 * np + o] = pre_ic * thermal_integral<KIND_IC_ELECTRON, Q>(c, T, L.xa10, ulim);
-        }
-        if (L.xb11 > L.xa11 && !(Ep < kMe2 / (50.0 * T))) {
-            const double ulim = fmin(L.xb11, xmax);
-            if (ulim > L.xa11 && !shared_regime(L.xa11, L.xb11, T, p.Ephb_T_max, x_bot, Tmin)) {
-                const double add = pre_pc * thermal_integral<KIND_PC_ELECTRON, Q>(c, T, L.xa11, ulim);
-                Kws[3 * np + o] += add;
-                Kws[2 * np + o] += add;
-            }
-        }
+    {   // e -> e
+        range(L.xa10, L.xb10, L.xa10 > 0.0, 0, t_lo, n);
+        wien_pooled<KIND_IC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa10, L.xb10, E, Ep - E, 0.25 * kMe2 / Ep, 0.5 / Ep, pre_ic, loc, lane, smask, spref);
+    }
+    {   // gamma -> e (pair creation): needs E' >= me^2/(50 T)
+        const int t_pc = first_true(Tg, nt, [&](double T) { return !(Ep < kMe2 / (50.0 * T)); });
+        range(L.xa11, L.xb11, true, t_pc, t_lo, n);
+        wien_pooled<KIND_PC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa11, L.xb11, E, Ep, 0.0, 0.0, pre_pc, loc, lane, smask, spref);
     }
 }
 
