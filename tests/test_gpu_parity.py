@@ -214,7 +214,8 @@ def test_linearity_in_sources(gpu_engine, results):
         live = (r["pdi"] > 1e-6 * r["pdi"].max(axis=1, keepdims=True)) & rows[:, None]
         dev = np.abs(r2["pdi"][live] / (8.0 * r["pdi"][live]) - 1.0)
         assert dev.max() < tol, (name, dev.max(), r["pdi"][live][dev.argmax()])
-        assert np.allclose(r2["mpdi"][0], 8.0 * r["mpdi"][0], rtol=10 * tol, atol=0)
+        big = np.abs(r["mpdi"][0]) > 1e-30      # entries built from floored rates (1e-200) do not scale
+        assert np.allclose(r2["mpdi"][0][big], 8.0 * r["mpdi"][0][big], rtol=10 * tol, atol=0)
 
 
 def test_c_abi_host_entry(gpu_engine, results):
