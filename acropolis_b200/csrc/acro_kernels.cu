@@ -28,12 +28,12 @@ namespace acro {
 __constant__ double c_sig[ACRO_NR][4];    // generic reactions: {log(N Q^p1), p2, p3, Q}
 __constant__ double c_sig2[2][3];         // second power-law terms of reactions 13 and 16: {log(N Q^p1), p2, p3}
 
-constexpr int kGLTotal = 8 + 16 + 32 + 64 + 96 + 128;
+constexpr int kGLTotal = 8 + 16 + 32 + 64 + 96 + 128 + 12;
 __constant__ double c_glx[kGLTotal];
 __constant__ double c_glw[kGLTotal];
 
 __host__ __device__ constexpr int gl_offset(int order) {
-    return order == 8 ? 0 : order == 16 ? 8 : order == 32 ? 24 : order == 64 ? 56 : order == 96 ? 120 : 216;
+    return order == 8 ? 0 : order == 16 ? 8 : order == 32 ? 24 : order == 64 ? 56 : order == 96 ? 120 : order == 128 ? 216 : 344;   // 344: order 12
 }
 
 }  // namespace acro
@@ -87,7 +87,7 @@ static void gauss_legendre(int n, double* x, double* w) {
 
 cudaError_t upload_quadrature_tables() {
     std::vector<double> x(kGLTotal), w(kGLTotal);
-    const int orders[6] = {8, 16, 32, 64, 96, 128};
+    const int orders[7] = {8, 16, 32, 64, 96, 128, 12};
     for (int o : orders) gauss_legendre(o, x.data() + gl_offset(o), w.data() + gl_offset(o));
     cudaError_t e = cudaMemcpyToSymbol(c_glx, x.data(), sizeof(double) * kGLTotal);
     if (e != cudaSuccess) return e;

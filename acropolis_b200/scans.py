@@ -173,9 +173,15 @@ def run_points(model, param_sets, devices=None, group=256):
             rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
 
     ncol = 3
-    for g0 in range(0, N, group):
+    # group boundaries: a small first group gets the GPU going early, then `group` points at a time
+    bounds, g0 = [], 0
+    while g0 < N:
+        g1 = min(N, g0 + (max(32, group // 4) if not bounds else group))
+        bounds.append((g0, g1))
+        g0 = g1
+    for g0, g1 in bounds:
         idx, todo = [], []
-        for i in range(g0, min(g0 + group, N)):
+        for i in range(g0, g1):
             m = model(**param_sets[i])
             ncol = m._sII.bbn_abundances().shape[1]
             if m.is_trivial():
