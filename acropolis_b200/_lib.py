@@ -30,7 +30,7 @@ class Tables(C.Structure):
 class Params(C.Structure):
     _fields_ = [("quad_order", C.c_int32), ("pdi_cell_order", C.c_int32), ("Emin", C.c_double),
                 ("approx_zero", C.c_double), ("Ephb_T_max", C.c_double), ("E_EC_max", C.c_double),
-                ("use_db", C.c_int32), ("kernel_mode", C.c_int32)]
+                ("use_db", C.c_int32), ("kernel_mode", C.c_int32), ("wien_from", C.c_double)]
 
 
 class Batch(C.Structure):
@@ -50,7 +50,7 @@ class Out(C.Structure):
 
 EXPORTS = ("acro_abi_version", "acro_default_params", "acro_create", "acro_destroy", "acro_last_error", "acro_set_params",
            "acro_workspace_bytes", "acro_run_batch", "acro_run_batch_host", "acro_unpack_kernels", "acro_matp_batch",
-           "acro_transfer_batch", "acro_total_rates", "acro_measure_fp64_peak", "acro_last_stage_ms", "acro_launch_count",
+           "acro_transfer_batch", "acro_total_rates", "acro_measure_fp64_peak", "acro_last_stage_ms", "acro_last_kernel_split_ms", "acro_launch_count",
            "acro_count_work")
 
 _lib = None
@@ -84,12 +84,13 @@ def load():
     lib.acro_total_rates.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.acro_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.acro_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
+    lib.acro_last_kernel_split_ms.argtypes = [vp, C.POINTER(C.c_float * 2)]
     lib.acro_count_work.argtypes = [vp, C.POINTER(Batch), C.POINTER(C.c_int64 * 4), vp]
     lib.acro_launch_count.argtypes = [vp]
     lib.acro_launch_count.restype = i64
     for name in EXPORTS:
         getattr(lib, name)
-    if lib.acro_abi_version() != 1:
+    if lib.acro_abi_version() != 2:
         raise ImportError("acropolis_b200: ABI version mismatch in %s" % LIB_PATH)
     _lib = lib
     return lib

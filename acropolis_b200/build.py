@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", f) for f in ("acro_kernels.cu", "acro_api.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("acro_internal.h", "acro_physics.cuh")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))] + \
     [os.path.join(HERE, "..", "include", "acropolis_b200.h")]
 OUT = os.path.join(HERE, "libacropolis_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -30,16 +30,18 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build_library(force=False, verbose=False):
-    if not force and up_to_date():
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """``out``/``defines`` build a variant library next to the product one (kernel A/B runs, tools/)."""
+    if out is None and not force and up_to_date():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    out = OUT if out is None else out
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -50,6 +50,7 @@ void acro_default_params(acro_params_t* p) {
     p->E_EC_max = 10.0;
     p->use_db = 1;
     p->kernel_mode = ACRO_KERNELS_FAST;
+    p->wien_from = 7.38905609893065;
 }
 
 static int check_params(acro_handle* h, const acro_params_t* p) {
@@ -57,6 +58,7 @@ static int check_params(acro_handle* h, const acro_params_t* p) {
         return fail(h, ACRO_EINVAL, "quad_order must be 16, 32, 64 or 96");
     if (!(p->pdi_cell_order == 8 || p->pdi_cell_order == 16)) return fail(h, ACRO_EINVAL, "pdi_cell_order must be 8 or 16");
     if (!(p->kernel_mode == ACRO_KERNELS_FAST || p->kernel_mode == ACRO_KERNELS_PLAIN_GL || p->kernel_mode == ACRO_KERNELS_PER_T)) return fail(h, ACRO_EINVAL, "bad kernel_mode");
+    if (!(p->wien_from >= 2.718281828459045 && p->wien_from <= 7.38905609893066)) return fail(h, ACRO_EINVAL, "wien_from must lie in [e, e^2]");
     if (!(p->Emin > 0 && p->approx_zero > 0 && p->Ephb_T_max > 0 && p->E_EC_max > 0)) return fail(h, ACRO_EINVAL, "bad params");
     return ACRO_OK;
 }
@@ -94,6 +96,7 @@ int acro_create(acro_handle_t** out, int device, const acro_tables_t* t, const a
     d.eta = t->eta; d.Yp = t->Y0[1 * 3 + 0]; d.YHe4 = t->Y0[5 * 3 + 0];
     for (int i = 0; i < 27; ++i) d.Y0[i] = t->Y0[i];
     for (int i = 0; i < 5; ++i) cudaEventCreate(&h->ev[i]);
+    cudaEventCreate(&h->lc.split);
     *out = h;
     return ACRO_OK;
 }
@@ -103,6 +106,7 @@ int acro_destroy(acro_handle_t* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_ratedb); cudaFree(h->d_cosmo_lT); cudaFree(h->d_cosmo_ld);
     for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->lc.split) cudaEventDestroy(h->lc.split);
     delete h;
     return ACRO_OK;
 }
@@ -199,6 +203,15 @@ int acro_last_stage_ms(acro_handle_t* h, float ms[4]) {
     if (!h->ev_valid) return fail(h, ACRO_EINVAL, "no batch has been run");
     CU(h, cudaEventSynchronize(h->ev[4]));
     for (int i = 0; i < 4; ++i) CU(h, cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+    return ACRO_OK;
+}
+
+int acro_last_kernel_split_ms(acro_handle_t* h, float ms[2]) {
+    if (!h || !ms) return ACRO_EINVAL;
+    if (!h->ev_valid || !h->lc.split_valid) return fail(h, ACRO_EINVAL, "the production kernel builder has not run on this handle");
+    CU(h, cudaEventSynchronize(h->ev[2]));
+    CU(h, cudaEventElapsedTime(&ms[0], h->ev[1], h->lc.split));
+    CU(h, cudaEventElapsedTime(&ms[1], h->lc.split, h->ev[2]));
     return ACRO_OK;
 }
 

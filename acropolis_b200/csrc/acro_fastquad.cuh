@@ -19,6 +19,15 @@
 #ifndef ACRO_FQ_UNROLL
 #define ACRO_FQ_UNROLL 1
 #endif
+#ifndef ACRO_FQ_ESTRIN
+#define ACRO_FQ_ESTRIN 1
+#endif
+#ifndef ACRO_FQ_LAGSHIFT
+#define ACRO_FQ_LAGSHIFT 0
+#endif
+#ifndef ACRO_FQ_LOGTAB
+#define ACRO_FQ_LOGTAB 1
+#endif
 #define ACRO_PRAGMA(x) _Pragma(#x)
 #define ACRO_UNROLL(n) ACRO_PRAGMA(unroll n)
 
@@ -38,10 +47,15 @@ constexpr double kSteepSpan = 32.0;             // and the span (x_b - x_a)/T mu
 __device__ __forceinline__ double frcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if ACRO_FQ_ESTRIN
+    const double e = fma(-x, y, 1.0);      // seed error ~2^-20: one cubic step y (1 + e + e^2) leaves e^3
+    return fma(y, fma(e, e, e), y);
+#else
     double e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
+#endif
 }
 
 // Polynomial coefficients live in constant memory so that every FMA takes its constant straight from the constant bank
@@ -64,9 +78,18 @@ __device__ __forceinline__ double fexp(double x) {
     const double kf = t - 6755399441055744.0;
     double r = fma(kf, c_exp_rr[1], x);
     r = fma(kf, c_exp_rr[2], r);
+#if ACRO_FQ_ESTRIN
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;   // Estrin: dependency depth 4 instead of 13
+    const double a0 = fma(c_exp[1], r, c_exp[0]), a1 = fma(c_exp[3], r, c_exp[2]), a2 = fma(c_exp[5], r, c_exp[4]),
+                 a3 = fma(c_exp[7], r, c_exp[6]), a4 = fma(c_exp[9], r, c_exp[8]), a5 = fma(c_exp[11], r, c_exp[10]),
+                 a6 = fma(c_exp[13], r, c_exp[12]);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double p = fma(fma(a6, r4, b2), r8, fma(b1, r4, b0));
+#else
     double p = c_exp[13];
 #pragma unroll
     for (int i = 12; i >= 0; --i) p = fma(p, r, c_exp[i]);
+#endif
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
@@ -80,11 +103,40 @@ __device__ __forceinline__ double flog(double x) {
     const double m = __hiloint2double(hi, lo);
     const double f = (m - 1.0) * frcp(m + 1.0);
     const double f2 = f * f;
+#if ACRO_FQ_ESTRIN
+    const double z2 = f2 * f2, z4 = z2 * z2;    // polynomial in z = f^2: depth 4 instead of 9
+    const double a0 = fma(c_log[1], f2, c_log[0]), a1 = fma(c_log[3], f2, c_log[2]), a2 = fma(c_log[5], f2, c_log[4]),
+                 a3 = fma(c_log[7], f2, c_log[6]), a4 = fma(c_log[9], f2, c_log[8]);
+    const double p = fma(fma(a4, z4, fma(a3, z2, a2)), z4, fma(a1, z2, a0));
+#else
     double p = c_log[9];
 #pragma unroll
     for (int i = 8; i >= 0; --i) p = fma(p, f2, c_log[i]);
+#endif
     const double ef = (double)e;
     return fma(ef, c_ln2[0], fma(p, f, ef * c_ln2[1]));
+}
+
+// Table-driven log for the node loops: x = 2^e m, m in [1,2) falls into one of 128 intervals with centre c_i; with
+// (u_i, v_i) = (1/c_i, -log u_i - [i >= 53] ln 2) -- the second term moves m >= sqrt(2) to the exponent above so that nothing
+// cancels around x = 1 -- log x = (e + [i >= 53]) ln 2 + v_i + log1p(m u_i - 1), |m u_i - 1| < 4e-3, series to r^7 (< 2e-20).
+// 10 FP64 operations on a dependency chain of 9 (atanh form above: 17 on a chain of 19, plus the reciprocal seed).
+constexpr int kLogTab = 128, kLogTabSplit = 53;
+__device__ double2 g_logtab[kLogTab];
+__constant__ double c_l1p[6] = {-1.0 / 2.0, 1.0 / 3.0, -1.0 / 4.0, 1.0 / 5.0, -1.0 / 6.0, 1.0 / 7.0};
+
+__device__ __forceinline__ double flog_tab(double x, const double2* __restrict__ lt) {
+    const int hi = __double2hiint(x);
+    const int i = (hi >> 13) & (kLogTab - 1);
+    const int e = (hi >> 20) - 1023 + (i >= kLogTabSplit ? 1 : 0);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double2 uv = lt[i];
+    const double r = fma(m, uv.x, -1.0);
+    double p = c_l1p[5];
+#pragma unroll
+    for (int k = 4; k >= 0; --k) p = fma(p, r, c_l1p[k]);
+    const double ef = (double)e;
+    return fma(ef, c_ln2[0], (uv.y + fma(r * r, p, r)) + ef * c_ln2[1]);
 }
 
 // 1/(e^v - 1), v > 0
@@ -107,7 +159,16 @@ struct PairConst {   // per-(E,E') constants of the three integrands
     double c9;        // r^2/(2+2r), r = E/(E'-E)
     double c10;       // me^2/(4 E')
     double i2Ep;      // 1/(2 E')
+#if ACRO_FQ_LOGTAB
+    const double2* lt;   // log table (shared-memory copy of g_logtab where the kernel stages one)
+#endif
 };
+
+#if ACRO_FQ_LOGTAB
+#define ACRO_NODE_LOG(c, v) flog_tab((v), (c).lt)
+#else
+#define ACRO_NODE_LOG(c, v) flog(v)
+#endif
 
 // integrand WITHOUT the Bose factor and without the power of x that goes with it:
 //   IC kernels:  F(...)            (the measure supplies x^2 dlogx = x dx)
@@ -117,7 +178,7 @@ __device__ __forceinline__ double integrand_core(const PairConst& c, double x, d
                                                  bool have_log) {
     if (KIND == KIND_IC_PHOTON) {
         const double q = x_a * frcp(x);
-        const double lq = have_log ? -lnx_minus_lnxa : flog(q);
+        const double lq = have_log ? -lnx_minus_lnxa : ACRO_NODE_LOG(c, q);
         const double omq = 1.0 - q;
         return fma(2.0 * q, lq, fma(fma(2.0, q, 1.0), omq, c.c9 * omq));
     } else if (KIND == KIND_IC_ELECTRON) {
@@ -125,13 +186,13 @@ __device__ __forceinline__ double integrand_core(const PairConst& c, double x, d
         const double ixb = frcp(x * B);
         const double q = c.c10 * A * ixb;
         const double omq = 1.0 - q;
-        return fma(2.0 * q, flog(q), fma(fma(2.0, q, 1.0), omq, A * A * omq * c.i2Ep * (x * ixb)));
+        return fma(2.0 * q, ACRO_NODE_LOG(c, q), fma(fma(2.0, q, 1.0), omq, A * A * omq * c.i2Ep * (x * ixb)));
     } else {
         const double s = c.Ep + x, Eep = s - c.E, ee = c.E * Eep;
         const double R = frcp(ee * s * x);
         const double iee = R * s * x, is = R * ee * x, ix = R * ee * s;
         const double s2 = s * s;
-        double sud = 4.0 * s2 * flog(4.0 * x * ee * is * (1.0 / kMe2)) * iee;
+        double sud = 4.0 * s2 * ACRO_NODE_LOG(c, 4.0 * x * ee * is * (1.0 / kMe2)) * iee;
         sud = fma(fma(kMe2 * ix, is, -1.0), (s2 * s2) * (iee * iee), sud);
         sud = fma(2.0 * fma(2.0 * x, s, -kMe2), s2 * iee * (1.0 / kMe2), sud);
         return fma(-8.0 * (1.0 / kMe2), x * s, sud);
@@ -149,12 +210,20 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
         //   va in (e, e^1.5]: 24   (e^1.5, e^2]: 16   (e^2, e^2.5]: 12   (e^2.5, e^3]: 8   (e^3, e^4]: 6   > e^4: 4
         const double Ea = fexp(-va);
         int n, off;
+#if ACRO_FQ_LAGSHIFT   // experiment: one order lower in every band
+        if (va > 20.085536923187668) { n = 4; off = 0; }
+        else if (va > 12.182493960703473) { n = 6; off = 4; }
+        else if (va > 7.38905609893065) { n = 8; off = 10; }
+        else if (va > 4.4816890703380645) { n = 12; off = 18; }
+        else { n = 16; off = 30; }
+#else
         if (va > 54.598150033144236) { n = 4; off = 0; }
         else if (va > 20.085536923187668) { n = 6; off = 4; }
         else if (va > 12.182493960703473) { n = 8; off = 10; }
         else if (va > 7.38905609893065) { n = 12; off = 18; }
         else if (va > 4.4816890703380645) { n = 16; off = 30; }
         else { n = 24; off = 46; }
+#endif
         double sum = 0.0;
 #pragma unroll 1
         for (int kk = 0; kk < n; ++kk) {

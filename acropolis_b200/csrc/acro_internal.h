@@ -30,6 +30,8 @@ struct DirectRateItem {
 
 struct LaunchCounters {
     int64_t launches = 0;
+    cudaEvent_t split = nullptr;   // recorded between the two launches of the production kernel builder
+    bool split_valid = false;
 };
 
 // Kernel launchers (acro_kernels.cu).  All asynchronous on `st`; return cudaGetLastError().

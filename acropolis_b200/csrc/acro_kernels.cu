@@ -28,12 +28,12 @@ namespace acro {
 __constant__ double c_sig[ACRO_NR][4];    // generic reactions: {log(N Q^p1), p2, p3, Q}
 __constant__ double c_sig2[2][3];         // second power-law terms of reactions 13 and 16: {log(N Q^p1), p2, p3}
 
-constexpr int kGLTotal = 8 + 16 + 32 + 64 + 96 + 128 + 12;
+constexpr int kGLTotal = 8 + 16 + 32 + 64 + 96 + 128 + 12 + 10;
 __constant__ double c_glx[kGLTotal];
 __constant__ double c_glw[kGLTotal];
 
 __host__ __device__ constexpr int gl_offset(int order) {
-    return order == 8 ? 0 : order == 16 ? 8 : order == 32 ? 24 : order == 64 ? 56 : order == 96 ? 120 : order == 128 ? 216 : 344;   // 344: order 12
+    return order == 8 ? 0 : order == 16 ? 8 : order == 32 ? 24 : order == 64 ? 56 : order == 96 ? 120 : order == 128 ? 216 : order == 12 ? 344 : 356;   // 356: order 10
 }
 
 }  // namespace acro
@@ -87,7 +87,7 @@ static void gauss_legendre(int n, double* x, double* w) {
 
 cudaError_t upload_quadrature_tables() {
     std::vector<double> x(kGLTotal), w(kGLTotal);
-    const int orders[7] = {8, 16, 32, 64, 96, 128, 12};
+    const int orders[8] = {8, 16, 32, 64, 96, 128, 12, 10};
     for (int o : orders) gauss_legendre(o, x.data() + gl_offset(o), w.data() + gl_offset(o));
     cudaError_t e = cudaMemcpyToSymbol(c_glx, x.data(), sizeof(double) * kGLTotal);
     if (e != cudaSuccess) return e;
@@ -103,6 +103,15 @@ cudaError_t upload_quadrature_tables() {
     if ((e = cudaMemcpyToSymbol(c_lag_s, ls, sizeof(ls))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_lag_w, lw, sizeof(lw))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_lag_es, les, sizeof(les))) != cudaSuccess) return e;
+    {   // log table of flog_tab (acro_fastquad.cuh): u_i = 1/c_i as a double, v_i = -log(u_i) - [i >= split] ln 2 in long double
+        double2 lt[kLogTab];
+        for (int i = 0; i < kLogTab; ++i) {
+            const double u = 1.0 / (1.0 + (i + 0.5) / kLogTab);
+            lt[i].x = u;
+            lt[i].y = (double)(-logl((long double)u) - (i >= kLogTabSplit ? logl(2.0L) : 0.0L));
+        }
+        if ((e = cudaMemcpyToSymbol(g_logtab, lt, sizeof(lt))) != cudaSuccess) return e;
+    }
     // Legendre tables of the 16-node panels (acro_tshared.cuh)
     double modal[kPanN][kPanN], rec[kPanN][2];
     const double* gx = x.data() + gl_offset(kPanN);
@@ -417,6 +426,9 @@ __device__ __forceinline__ KernelEntry eval_kernels_fast(double E, double Ep, do
     const double xmax = Ephb_T_max * T;
     PairConst c;
     c.E = E; c.Ep = Ep; c.dE = Ep - E;
+#if ACRO_FQ_LOGTAB
+    c.lt = g_logtab;
+#endif
     k.gg = kernel_photon_photon(E, Ep, T) + kernel_compton_core(E, Ep, d.ne);
     k.eg = 0.0;
     k.ee = 0.0;
@@ -426,7 +438,7 @@ __device__ __forceinline__ KernelEntry eval_kernels_fast(double E, double Ep, do
         const double ulim = fmin(L.xb9, xmax);
         if (ulim > L.xa9) {
             double I;
-            if (si.on && shared_regime(L.xa9, L.xb9, T, Ephb_T_max, si.x_bot, si.Tmin)) I = raw[1 * np];
+            if (si.on && shared_regime(L.xa9, kSteepX, T, si.x_bot, si.Tmin)) I = raw[1 * np];
             else {
                 const double r = E / c.dE;
                 c.c9 = r * r / (2.0 + 2.0 * r);
@@ -439,7 +451,7 @@ __device__ __forceinline__ KernelEntry eval_kernels_fast(double E, double Ep, do
         const double ulim = fmin(L.xb10, xmax);
         if (ulim > L.xa10) {
             double I;
-            if (si.on && shared_regime(L.xa10, L.xb10, T, Ephb_T_max, si.x_bot, si.Tmin)) I = raw[4 * np];
+            if (si.on && shared_regime(L.xa10, kSteepX, T, si.x_bot, si.Tmin)) I = raw[4 * np];
             else {
                 c.c10 = 0.25 * kMe2 / Ep;
                 c.i2Ep = 0.5 / Ep;
@@ -454,7 +466,7 @@ __device__ __forceinline__ KernelEntry eval_kernels_fast(double E, double Ep, do
         const double ulim = fmin(L.xb11, xmax);
         if (ulim > L.xa11) {
             double I;
-            if (si.on && shared_regime(L.xa11, L.xb11, T, Ephb_T_max, si.x_bot, si.Tmin)) I = raw[3 * np];
+            if (si.on && shared_regime(L.xa11, kSteepX, T, si.x_bot, si.Tmin)) I = raw[3 * np];
             else I = thermal_integral<KIND_PC_ELECTRON, Q>(c, T, L.xa11, ulim);
             pair += 0.25 * kPi * (kAlpha * kAlpha) * kMe2 * I / (Ep * Ep * Ep);
         }
@@ -1154,6 +1166,7 @@ cudaError_t set_half_range(double v) { return cudaMemcpyToSymbol(c_half_range, &
 
 cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const acro_params_t& p, double* Kws,
                            cudaStream_t st, LaunchCounters& lc) {
+    lc.split_valid = false;
     if (b.n_pairs_total == 0) return cudaSuccess;
     if (const char* hr = getenv("ACRO_HALF_RANGE")) {   // experiment knob (A/B runs only)
         static double last = -1.0;
@@ -1171,7 +1184,8 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
         }
     } else {
         if (p.kernel_mode == ACRO_KERNELS_FAST) {   // the production kernel builder (acro_tshared.cuh): all five planes
-            const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT + 4 * kTT);
+            const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT + (kTileScalars + 1) * kTT + (ACRO_FQ_LOGTAB ? 2 * kLogTab : 0) +
+                                                 (size_t)kTT * kSharedThreads);
             const int64_t tri_max = (int64_t)b.ne_max * (b.ne_max + 1) / 2;
             dim3 grid((unsigned)((tri_max + kSharedThreads - 1) / kSharedThreads), (unsigned)b.n_points);
             cudaError_t e = cudaSuccess;
@@ -1184,6 +1198,7 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
             kernels_shared_kernel<<<grid, kSharedThreads, smem, st>>>(b, Kws, t, p);
             lc.launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if (lc.split) lc.split_valid = cudaEventRecord(lc.split, st) == cudaSuccess;
             dim3 gw((unsigned)((tri_max + 127) / 128), (unsigned)b.n_points);
             switch (p.quad_order) {
                 case 16: kernels_wien_kernel<16><<<gw, 128, 0, st>>>(b, Kws, p); break;

@@ -23,8 +23,12 @@
 
 namespace acro {
 
+constexpr int kTileScalars = 8;   // per-temperature scalars of a tile kept in shared memory (kernels_shared_kernel)
 #ifndef ACRO_TS_UNROLL
 #define ACRO_TS_UNROLL 1
+#endif
+#ifndef ACRO_TS_FISSION
+#define ACRO_TS_FISSION 2
 #endif
 #ifndef ACRO_TS_HC
 #define ACRO_TS_HC 2.0
@@ -84,9 +88,9 @@ __device__ __forceinline__ void panel_geom(const SharedGrid& g, int pn, double& 
 }
 
 // (pair, T) combinations served by the shared grid; evaluated identically by producer and consumer
-__device__ __forceinline__ bool shared_regime(double x_a, double x_b0, double T, double Ephb_T_max, double x_grid_bot, double T_min) {
-    (void)x_b0; (void)Ephb_T_max;
-    return (x_a <= kSteepX * T) && (x_a >= x_grid_bot || x_grid_bot <= 2e-11 * T_min);
+// (wien_from = acro_params_t.wien_from, e <= wien_from <= e^2: above it the combination goes to kernels_wien_kernel)
+__device__ __forceinline__ bool shared_regime(double x_a, double wien_from, double T, double x_grid_bot, double T_min) {
+    return (x_a <= wien_from * T) && (x_a >= x_grid_bot || x_grid_bot <= 2e-11 * T_min);
 }
 
 struct PairLimits {           // T-independent limits of the three integrals of one pair; x_a < 0 marks "no range"
@@ -227,6 +231,42 @@ __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, 
             }
         }
         if (__any_sync(0xffffffffu, full)) {
+#if ACRO_TS_FISSION
+            // Node values first, accumulation second: the kPanN evaluations are independent dependency chains that the
+            // scheduler can interleave (two warps per scheduler cannot hide one chain behind another warp's).  Branch-free:
+            // lanes without this panel carry weight 0 and finite arguments.
+            const double wscale = full ? 0.5 * h : 0.0;
+            constexpr int kGroup = ACRO_TS_FISSION;     // nodes evaluated together
+            static_assert(kPanN % kGroup == 0, "node group must divide the panel");
+#pragma unroll 1
+            for (int m0 = 0; m0 < kPanN; m0 += kGroup) {
+            double fv[kGroup];
+#pragma unroll
+            for (int mm = 0; mm < kGroup; ++mm) {
+                const int m = m0 + mm;
+                const int k = base + m;
+                const double x = sx[k];
+                double f;
+                if (KIND == KIND_IC_PHOTON) {
+                    const double q = x_a * six[k];
+                    const double omq = 1.0 - q;
+                    f = fma(2.0 * q, lna - sy[k], fma(fma(2.0, q, 1.0), omq, c.c9 * omq));
+                } else if (KIND == KIND_IC_ELECTRON) {
+                    f = integrand_core<KIND_IC_ELECTRON>(c, x, x_a, 0.0, false);
+                } else {   // the table holds x^2/(e^{x/T}-1); the pair-creation integrand carries x^1
+                    f = integrand_core<KIND_PC_ELECTRON>(c, x, x_a, 0.0, false) * six[k];
+                }
+                fv[mm] = full ? f * (c_glw[gl_offset(kPanN) + m] * wscale) : 0.0;
+            }
+#pragma unroll
+            for (int mm = 0; mm < kGroup; ++mm) {
+                const double* __restrict__ Bk = sB + (size_t)(base + m0 + mm) * kTT;
+                const double f = fv[mm];
+#pragma unroll
+                for (int t = 0; t < kTT; ++t) acc[t] = fma(f, Bk[t], acc[t]);
+            }
+            }
+#else
             const double wscale = 0.5 * h;
             ACRO_UNROLL(ACRO_TS_UNROLL)
             for (int m = 0; m < kPanN; ++m) {
@@ -249,6 +289,7 @@ __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, 
 #pragma unroll
                 for (int t = 0; t < kTT; ++t) acc[t] = fma(f, Bk[t], acc[t]);
             }
+#endif
         }
     }
 }
@@ -274,6 +315,14 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
     double* sy = six + kMaxPan * kPanN;
     double* sB = sy + kMaxPan * kPanN;                 // [nn][kTT]
     double* sT = sB + (size_t)kMaxPan * kPanN * kTT;   // per-temperature scalars of the tile: T, ne, nNZ2, photon-photon prefactor
+    int64_t* sK = reinterpret_cast<int64_t*>(sT + kTileScalars * kTT);   // plane offsets of the tile's systems
+#if ACRO_FQ_LOGTAB
+    double2* s_lt = reinterpret_cast<double2*>(sT + (kTileScalars + 1) * kTT);
+    for (int k = threadIdx.x; k < kLogTab; k += blockDim.x) s_lt[k] = g_logtab[k];
+    double* sA = reinterpret_cast<double*>(s_lt + kLogTab);   // [kTT][kSharedThreads] accumulators on their way out
+#else
+    double* sA = sT + (kTileScalars + 1) * kTT;
+#endif
     for (int k = threadIdx.x; k < nn; k += blockDim.x) {
         double lo, h;
         panel_geom(g, k / kPanN, lo, h);
@@ -302,6 +351,9 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
         c.c10 = 0.25 * kMe2 / Ep;
         c.i2Ep = 0.5 / Ep;
     }
+#if ACRO_FQ_LOGTAB
+    c.lt = s_lt;
+#endif
     const PairLimits L = pair_limits(E, Ep);
     const double x_bot = exp(g.y_bot);
     const int64_t np = b.n_pairs_total;
@@ -316,14 +368,26 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
     const double compton_e = kernel_compton_core(Ep + kMe - E, Ep, 1.0);
     const double bh_pair = (L.xa9 > 0.0) ? bh_dsdE_Z2(E, Ep) : 0.0;         // same condition E' >= E + me
 
+    // the lowest grid node is below every lower limit that matters (shared_regime(), second clause)
+    const bool deep = x_bot <= 2e-11 * Tmin;
+    const bool has9 = active && L.xa9 > 0.0, has10 = active && L.xa10 > 0.0, has11 = active && L.xb11 > L.xa11;
+    const bool reg9 = has9 && (deep || L.xa9 >= x_bot), reg10 = has10 && (deep || L.xa10 >= x_bot),
+               reg11 = has11 && (deep || L.xa11 >= x_bot);
+
     for (int t0 = 0; t0 < nt; t0 += kTT) {
         __syncthreads();
         if (threadIdx.x < kTT) {
             const int t = threadIdx.x;
-            const double T = b.sys_T[s0 + min(t0 + t, nt - 1)];
+            const int s = s0 + min(t0 + t, nt - 1);
+            const double T = b.sys_T[s];
             const Densities d = densities(T, tb.eta, tb.Yp, tb.YHe4);
             const double T3 = T * T * T;
             sT[t] = T; sT[kTT + t] = d.ne; sT[2 * kTT + t] = d.nNZ2; sT[3 * kTT + t] = T3 * T3;
+            sT[4 * kTT + t] = p.Ephb_T_max * T;       // thermal cut-off of the photon background
+            sT[5 * kTT + t] = p.wien_from * T;           // lower limits above this go to the Wien-tail kernel
+            sT[6 * kTT + t] = kMe2 / (50.0 * T);      // photon-photon pair creation switches on here (cascade.py:583)
+            sT[7 * kTT + t] = -T / kMe2;
+            sK[t] = b.sys_k_off[s];
         }
         __syncthreads();
         // Bose table of this temperature tile: raw x^2/(pi^2 (e^{x/T}-1)), zero above the cut-off 200 T
@@ -333,7 +397,7 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
             if (t0 + t < nt) {
                 const double T = sT[t];
                 const double x = sx[k];
-                if (x <= p.Ephb_T_max * T) v = x * x * bose_inv(x / T) * (1.0 / kPi2);
+                if (x <= sT[4 * kTT + t]) v = x * x * bose_inv(x / T) * (1.0 / kPi2);
             }
             sB[idx] = v;
         }
@@ -342,57 +406,61 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
         const int ntile = min(kTT, nt - t0);
         // a pair takes part in the shared integrals of this tile only if its lower limit is off the Wien tail for the
         // tile's highest temperature
-        const double xa_max = kSteepX * sT[ntile - 1];
+        const double xa_max = sT[5 * kTT + ntile - 1];
+        // Epilogues: acc[] must only ever be indexed with compile-time constants (a run-time index puts the accumulators
+        // into local memory for the whole kernel), and a 40-fold unrolled epilogue costs ~20 KB of code against a 6 KB L0
+        // instruction cache -- so the accumulators go through a thread-private shared-memory column and the store loops
+        // stay rolled.
+        double* __restrict__ myA = sA + threadIdx.x;
         // ---- e -> gamma (plane 1)
         {
-            const bool has = active && L.xa9 > 0.0;
-            const bool act = has && L.xb9 > L.xa9 && L.xa9 <= xa_max;
+            const bool act = has9 && L.xb9 > L.xa9 && L.xa9 <= xa_max;
             shared_integral<KIND_IC_PHOTON>(c, L.xa9, L.xb9, g, sx, six, sy, sB, act, acc);
-            if (active)
+#pragma unroll
+            for (int t = 0; t < kTT; ++t) myA[t * kSharedThreads] = acc[t];
+            if (active) {
+                double* __restrict__ out = Kws + 1 * np + loc;
                 for (int t = 0; t < ntile; ++t) {
-                    const double T = sT[t];
-                    double v = 0.0;
-                    if (has) {
-                        const double ulim = fmin(L.xb9, p.Ephb_T_max * T);
-                        if (ulim > L.xa9 && shared_regime(L.xa9, L.xb9, T, p.Ephb_T_max, x_bot, Tmin)) v = pre_ic * acc[t];
-                    }
-                    Kws[1 * np + b.sys_k_off[s0 + t0 + t] + loc] = v;
+                    const bool on = reg9 && fmin(L.xb9, sT[4 * kTT + t]) > L.xa9 && L.xa9 <= sT[5 * kTT + t];
+                    out[sK[t]] = on ? pre_ic * myA[t * kSharedThreads] : 0.0;
                 }
+            }
         }
         // ---- e -> e (plane 4)
         {
-            const bool has = active && L.xa10 > 0.0;
-            const bool act = has && L.xb10 > L.xa10 && L.xa10 <= xa_max;
+            const bool act = has10 && L.xb10 > L.xa10 && L.xa10 <= xa_max;
             shared_integral<KIND_IC_ELECTRON>(c, L.xa10, L.xb10, g, sx, six, sy, sB, act, acc);
-            if (active)
+#pragma unroll
+            for (int t = 0; t < kTT; ++t) myA[t * kSharedThreads] = acc[t];
+            if (active) {
+                double* __restrict__ out = Kws + 4 * np + loc;
                 for (int t = 0; t < ntile; ++t) {
-                    const double T = sT[t];
-                    double v = 0.0;
-                    if (has) {
-                        const double ulim = fmin(L.xb10, p.Ephb_T_max * T);
-                        if (ulim > L.xa10 && shared_regime(L.xa10, L.xb10, T, p.Ephb_T_max, x_bot, Tmin)) v = pre_ic * acc[t];
-                    }
-                    Kws[4 * np + b.sys_k_off[s0 + t0 + t] + loc] = v;
+                    const bool on = reg10 && fmin(L.xb10, sT[4 * kTT + t]) > L.xa10 && L.xa10 <= sT[5 * kTT + t];
+                    out[sK[t]] = on ? pre_ic * myA[t * kSharedThreads] : 0.0;
                 }
+            }
         }
         // ---- gamma -> e-/e+ (planes 2, 3) and gamma -> gamma (plane 0)
         {
-            const bool has = active && L.xb11 > L.xa11;
-            const bool act = has && L.xa11 <= xa_max && !(Ep < kMe2 / (50.0 * sT[ntile - 1]));
+            const bool act = has11 && L.xa11 <= xa_max && !(Ep < sT[6 * kTT + ntile - 1]);
             shared_integral<KIND_PC_ELECTRON>(c, L.xa11, L.xb11, g, sx, six, sy, sB, act, acc);
-            if (active)
+#pragma unroll
+            for (int t = 0; t < kTT; ++t) myA[t * kSharedThreads] = acc[t];
+            if (active) {
+                double* __restrict__ out = Kws + loc;
                 for (int t = 0; t < ntile; ++t) {
-                    const double T = sT[t], dne = sT[kTT + t], dnz = sT[2 * kTT + t];
-                    double pair = dnz * bh_pair;
-                    if (has && !(Ep < kMe2 / (50.0 * T))) {
-                        const double ulim = fmin(L.xb11, p.Ephb_T_max * T);
-                        if (ulim > L.xa11 && shared_regime(L.xa11, L.xb11, T, p.Ephb_T_max, x_bot, Tmin)) pair += pre_pc * acc[t];
-                    }
-                    const int64_t o = b.sys_k_off[s0 + t0 + t] + loc;
-                    Kws[3 * np + o] = pair;
-                    Kws[2 * np + o] = pair + dne * compton_e;
-                    Kws[0 * np + o] = pp_pair * sT[3 * kTT + t] * exp(-Ep * T / kMe2) + dne * compton_g;
+                    const double dne = sT[kTT + t];
+                    const bool on = reg11 && !(Ep < sT[6 * kTT + t]) && fmin(L.xb11, sT[4 * kTT + t]) > L.xa11 &&
+                                    L.xa11 <= sT[5 * kTT + t];
+                    const double pair = fma(sT[2 * kTT + t], bh_pair, on ? pre_pc * myA[t * kSharedThreads] : 0.0);
+                    const double arg = Ep * sT[7 * kTT + t];
+                    const double damp = arg > -700.0 ? fexp(arg) : 0.0;
+                    const int64_t o = sK[t];
+                    out[3 * np + o] = pair;
+                    out[2 * np + o] = fma(dne, compton_e, pair);
+                    out[o] = fma(pp_pair * sT[3 * kTT + t], damp, dne * compton_g);
                 }
+            }
         }
     }
 }
@@ -407,7 +475,7 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
 // pools its items: exclusive prefix sum of the range lengths, then 32 items at a time, each lane fetching the constants
 // of the owning pair with shuffles.
 #ifndef ACRO_WT_MINBLOCKS
-#define ACRO_WT_MINBLOCKS 6
+#define ACRO_WT_MINBLOCKS 8
 #endif
 
 // first index t in [0, nt) with pred(T[t]) true, for a predicate that is false...false true...true along the grid
@@ -434,7 +502,7 @@ template <int KIND, int Q>
 __device__ __forceinline__ void wien_pooled(const acro_batch_t& b, double* __restrict__ Kws, const acro_params_t& p, int s0, int nt,
                                             int t_lo, int n_mine, double x_a, double x_b0, double c0, double c1, double c2,
                                             double c3, double pre, long long loc, int lane, unsigned* __restrict__ smask,
-                                            int* __restrict__ spref) {
+                                            int* __restrict__ spref, const double2* __restrict__ lt) {
     const int64_t np = b.n_pairs_total;
     const int t_hi = t_lo + n_mine;
     int w_lo = n_mine > 0 ? t_lo : nt, w_hi = n_mine > 0 ? t_hi : 0;
@@ -487,6 +555,11 @@ __device__ __forceinline__ void wien_pooled(const acro_batch_t& b, double* __res
                 const double T = b.sys_T[s0 + t];
                 const double ulim = fmin(o_xb0, p.Ephb_T_max * T);
                 PairConst c;
+#if ACRO_FQ_LOGTAB
+                c.lt = lt;
+#else
+                (void)lt;
+#endif
                 if (KIND == KIND_IC_PHOTON) { c.c9 = o_c0; }
                 else if (KIND == KIND_IC_ELECTRON) { c.E = o_c0; c.dE = o_c1; c.c10 = o_c2; c.i2Ep = o_c3; }
                 else { c.E = o_c0; c.Ep = o_c1; }
@@ -511,6 +584,14 @@ __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(ac
     unsigned* smask = smask_all + (threadIdx.x >> 5) * kWienChunk;
     int* spref = spref_all + (threadIdx.x >> 5) * kWienChunk;
     const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#if ACRO_FQ_LOGTAB
+    __shared__ double2 s_lt[kLogTab];
+    for (int k = threadIdx.x; k < kLogTab; k += blockDim.x) s_lt[k] = g_logtab[k];
+    __syncthreads();
+    const double2* lt = s_lt;
+#else
+    const double2* lt = nullptr;
+#endif
     if (loc - lane >= tri) return;                     // whole warp beyond the point's pairs
     const bool valid = loc < tri;
     const int64_t locc = valid ? loc : tri - 1;
@@ -538,7 +619,7 @@ __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(ac
         if (!valid || !has || !(x_b0 > x_a)) return;
         const int t_ne = first_true(Tg, nt, [&](double T) { return fmin(x_b0, xf * T) > x_a; });
         const bool served = (x_a >= x_bot) || grid_full;
-        const int t_cut = served ? first_true(Tg, nt, [&](double T) { return x_a <= kSteepX * T; }) : nt;
+        const int t_cut = served ? first_true(Tg, nt, [&](double T) { return x_a <= p.wien_from * T; }) : nt;
         t_lo = max(t_ne, t_extra);
         n = max(0, t_cut - t_lo);
     };
@@ -546,16 +627,16 @@ __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(ac
     {   // e -> gamma
         range(L.xa9, L.xb9, L.xa9 > 0.0, 0, t_lo, n);
         const double r = E / fmax(Ep - E, 1e-300);
-        wien_pooled<KIND_IC_PHOTON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa9, L.xb9, r * r / (2.0 + 2.0 * r), 0.0, 0.0, 0.0, pre_ic, loc, lane, smask, spref);
+        wien_pooled<KIND_IC_PHOTON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa9, L.xb9, r * r / (2.0 + 2.0 * r), 0.0, 0.0, 0.0, pre_ic, loc, lane, smask, spref, lt);
     }
     {   // e -> e
         range(L.xa10, L.xb10, L.xa10 > 0.0, 0, t_lo, n);
-        wien_pooled<KIND_IC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa10, L.xb10, E, Ep - E, 0.25 * kMe2 / Ep, 0.5 / Ep, pre_ic, loc, lane, smask, spref);
+        wien_pooled<KIND_IC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa10, L.xb10, E, Ep - E, 0.25 * kMe2 / Ep, 0.5 / Ep, pre_ic, loc, lane, smask, spref, lt);
     }
     {   // gamma -> e (pair creation): needs E' >= me^2/(50 T)
         const int t_pc = first_true(Tg, nt, [&](double T) { return !(Ep < kMe2 / (50.0 * T)); });
         range(L.xa11, L.xb11, true, t_pc, t_lo, n);
-        wien_pooled<KIND_PC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa11, L.xb11, E, Ep, 0.0, 0.0, pre_pc, loc, lane, smask, spref);
+        wien_pooled<KIND_PC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa11, L.xb11, E, Ep, 0.0, 0.0, pre_pc, loc, lane, smask, spref, lt);
     }
 }
 

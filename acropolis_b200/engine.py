@@ -139,9 +139,9 @@ class Engine(object):
 
     def _sync_params(self):
         key = (params.quad_order, params.pdi_cell_order, params.Emin, params.approx_zero, params.Ephb_T_max,
-               params.E_EC_max, bool(flags.usedb and self._use_db), int(params.kernel_mode))
+               params.E_EC_max, bool(flags.usedb and self._use_db), int(params.kernel_mode), float(params.wien_from))
         if key != self._params_key:
-            p = _lib.Params(*key[:6], int(key[6]), key[7])
+            p = _lib.Params(*key[:6], int(key[6]), key[7], key[8])
             self._check(self.lib.acro_set_params(self.h, C.byref(p)), "acro_set_params")
             self._params_key = key
 
@@ -328,6 +328,12 @@ class Engine(object):
     def stage_ms(self):
         ms = (C.c_float * 4)()
         self._check(self.lib.acro_last_stage_ms(self.h, C.byref(ms)), "acro_last_stage_ms")
+        return np.array(list(ms), dtype=np.float64)
+
+    def kernel_split_ms(self):
+        """(temperature-shared kernel, Wien-tail kernel) device time [ms] of the last launch."""
+        ms = (C.c_float * 2)()
+        self._check(self.lib.acro_last_kernel_split_ms(self.h, C.byref(ms)), "acro_last_kernel_split_ms")
         return np.array(list(ms), dtype=np.float64)
 
     def _arena_for_chunk(self):

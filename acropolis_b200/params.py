@@ -42,4 +42,6 @@ NT_pd = 20             # temperature-grid points per decade
 quad_order = 64        # Gauss-Legendre nodes per thermal kernel integral (16, 32, 64, 96)
 pdi_cell_order = 8     # GL nodes per energy-grid cell of the pdi-rate integrals (8, 16)
 kernel_mode = 0        # 0: fast evaluation of the thermal kernel integrals (default); 1: plain Gauss-Legendre cross-check
+wien_from = 7.38905609893065   # x_a/T from which a thermal integral is done per temperature on the Wien tail (e .. e^2):
+                               # e^2 keeps every kernel entry within 1e-7 of the converged integral, e within 1e-9 (1.4x slower)
 workspace_bytes = None  # HBM budget [bytes] for the kernel planes of one chunk of points; None = 40% of free HBM (<= 64 GiB)

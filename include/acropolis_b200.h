@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ACRO_ABI_VERSION 1
+#define ACRO_ABI_VERSION 2
 
 #define ACRO_NX 3   /* cascade species: photon, electron, positron        (cascade.py:718)        */
 #define ACRO_NY 9   /* nuclides n,p,d,t,He3,He4,Li6,Li7,Be7              (nucl.py:32-42)          */
@@ -88,6 +88,10 @@ typedef struct {
     double  E_EC_max;        /* 10                                                                                */
     int32_t use_db;          /* flags.usedb                                                                       */
     int32_t kernel_mode;     /* ACRO_KERNELS_FAST (default) or ACRO_KERNELS_PLAIN_GL                              */
+    double  wien_from;       /* ACRO_KERNELS_FAST: a thermal integral whose lower limit x_a exceeds wien_from * T
+                              * is evaluated per (E,E',T) with Gauss-Laguerre on the Wien tail, the others on the
+                              * temperature-shared grid.  e <= wien_from <= e^2.  Default e^2 = 7.389 (kernel entries
+                              * within 1e-7 of the converged integrals); e = 2.718 gives 1e-9 at ~1.4x the time.    */
 } acro_params_t;
 
 /*
@@ -183,6 +187,9 @@ int acro_measure_fp64_peak(acro_handle_t* h, double* tflops);
 /* Device time [ms] of the last acro_run_batch stages on this handle (CUDA events on the launch stream):
  * ms[0]=rates, ms[1]=kernels, ms[2]=solve+pdi, ms[3]=matrix.  Synchronises on the recorded events.             */
 int acro_last_stage_ms(acro_handle_t* h, float ms[4]);
+
+/* Split of ms[1] for kernel_mode = ACRO_KERNELS_FAST: ms[0] = temperature-shared kernel, ms[1] = Wien-tail kernel. */
+int acro_last_kernel_split_ms(acro_handle_t* h, float ms[2]);
 
 /* Work census of a (device-resident) batch for the roofline's algorithmic-flop figure: out[0] = (system,i,j>=i) pairs,
  * out[1..3] = pairs with a non-empty range for the e->gamma, e->e and gamma->e thermal integrals (the reference's own

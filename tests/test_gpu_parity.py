@@ -20,10 +20,28 @@ POINTS = ["cfg1_decay", "decay_ee", "decay_nemin", "decay_mixed", "decay_lowT", 
 DIRECT = ("decay_lowT", "decay_highT")   # T grid leaves rates.db -> direct 2-D rate integrals
 
 
-@pytest.fixture(scope="module")
-def results(gpu_engine):
+E1 = float(np.e)
+
+
+class wien_from(object):
+    """Run a block with params.wien_from = v (include/acropolis_b200.h: acro_params_t.wien_from).  The default e^2 keeps
+    the kernel entries within 1e-7 of the converged integrals; e is the tight setting (1e-9)."""
+
+    def __init__(self, v):
+        self.v = v
+
+    def __enter__(self):
+        import acropolis_b200.params as params
+        self.old, params.wien_from = params.wien_from, self.v
+
+    def __exit__(self, *a):
+        import acropolis_b200.params as params
+        params.wien_from = self.old
+
+
+def _run_points(gpu_engine, names):
     out = {}
-    for name in POINTS + ["cfg1_decay_tight", "decay_ee_tight"]:
+    for name in names:
         z = golden(name + ".npz")
         sp = spec_from_golden(z)
         r = gpu_engine.run([sp], want=("G", "F", "pdi", "mpdi", "mdcy", "Yf", "status"))
@@ -31,6 +49,17 @@ def results(gpu_engine):
         r["G"], r["F"] = r["G"].reshape(NT, 3, NE), r["F"].reshape(NT, 3, NE)
         out[name] = (z, sp, r)
     return out
+
+
+@pytest.fixture(scope="module")
+def results(gpu_engine):
+    return _run_points(gpu_engine, POINTS + ["cfg1_decay_tight", "decay_ee_tight"])
+
+
+@pytest.fixture(scope="module")
+def results_tight(gpu_engine):
+    with wien_from(E1):
+        return _run_points(gpu_engine, ["cfg1_decay_tight", "decay_ee_tight"])
 
 
 @pytest.mark.parametrize("name", POINTS)
@@ -69,11 +98,17 @@ def test_kernel_planes_K(gpu_engine, name):
         K, G = gpu_engine.kernels_of(sp, int(it))
         Kr = z["K_it%d" % it]
         assert np.array_equal(K != 0, Kr != 0)                      # same support (thresholds, Compton edge, diagonal)
-        tol = 1e-9 if name.endswith("tight") else 1e-5              # reference at eps=1e-3 carries up to 2e-6 itself
-        assert relerr(K, Kr) < tol
+        # reference at eps=1e-3 carries up to 2e-6 itself; against the reference run at eps=1e-10 the default setting
+        # (wien_from = e^2) is good to 1e-7, measured 3e-8 (the bar of north_star is 1e-6)
+        assert relerr(K, Kr) < (1e-7 if name.endswith("tight") else 1e-5)
         assert relerr(K[0], Kr[0]) < 1e-13                              # closed forms: rounding level
         only_closed = (Kr[3] == 0)
         assert relerr(K[2][only_closed], Kr[2][only_closed]) < 1e-13
+        if name.endswith("tight"):
+            with wien_from(E1):
+                K1, _ = gpu_engine.kernels_of(sp, int(it))
+            assert np.array_equal(K1 != 0, Kr != 0)
+            assert relerr(K1, Kr) < 1e-9
 
 
 def test_kernel_planes_vs_converged_oracle(gpu_engine):
@@ -85,7 +120,11 @@ def test_kernel_planes_vs_converged_oracle(gpu_engine):
         Go, Ko = o.rates_kernels(sp.E_grid, float(sp.T[it]))
         assert np.array_equal(K != 0, Ko != 0)
         assert relerr(K, Ko) < 1e-6 and relerr(G, Go) < 1e-6
-        assert relerr(K, Ko) < 1e-9     # measured: GL-64 vs converged adaptive GK21
+        assert relerr(K, Ko) < 1e-7     # default wien_from = e^2
+        with wien_from(E1):
+            K1, _ = gpu_engine.kernels_of(sp, it)
+        assert np.array_equal(K1 != 0, Ko != 0)
+        assert relerr(K1, Ko) < 1e-9    # measured: tight setting vs converged adaptive GK21
 
 
 @pytest.mark.parametrize("name", POINTS)
@@ -96,9 +135,11 @@ def test_spectra_F(results, name):
 
 
 @pytest.mark.parametrize("name", ["cfg1_decay_tight", "decay_ee_tight"])
-def test_spectra_vs_tight_reference(results, name):
+def test_spectra_vs_tight_reference(results, results_tight, name):
     z, sp, r = results[name]
-    assert relerr(r["F"], z["F"]) < 1e-9
+    assert relerr(r["F"], z["F"]) < 1e-7          # default setting: measured 2e-9
+    z, sp, r = results_tight[name]
+    assert relerr(r["F"], z["F"]) < 1e-9          # wien_from = e
 
 
 @pytest.mark.parametrize("name", ["cfg1_decay", "decay_ee", "decay_nemin", "cfg2_annih"])

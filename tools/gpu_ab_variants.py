@@ -17,6 +17,8 @@ def planes(mode, order):
     ch = eng.stage(specs, ("Yf",), resident=True)
     for rep in range(3):
         eng.launch(ch, _lib.STAGE_RATES | _lib.STAGE_KERNELS); ms = eng.stage_ms()
+    if mode == 0:
+        print("   split shared/wien [ms]:", eng.kernel_split_ms().round(2).tolist(), flush=True)
     n = ch["cnt"]["n_pairs_total"]
     K = eng._ws[:5 * n * 8].view(torch.float64).clone().view(5, n)
     eng.launch(ch, _lib.STAGE_ALL); eng.stream.synchronize()
