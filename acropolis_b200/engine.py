@@ -31,16 +31,33 @@ class PointSpec(object):
         self.sc_E = sc_E    # SEPARABLE: [NE,3]
 
 
+_GRID_MEMO = {}     # the points of a grid scan share their energy and temperature grids (read-only arrays)
+
+
+def _memo_grid(key, make):
+    g = _GRID_MEMO.get(key)
+    if g is None:
+        if len(_GRID_MEMO) >= 8192:
+            _GRID_MEMO.clear()
+        g = _GRID_MEMO[key] = make()
+        g.setflags(write=False)
+    return g
+
+
 def energy_grid(E0):
     """NE and E_grid exactly as cascade.py:736-745 (same numpy/math expressions => bit-identical grid)."""
-    NE = max(int(log10(E0 / params.Emin) * params.NE_pd), params.NE_min)
-    return np.logspace(log(params.Emin), log(E0), NE, base=np.e)
+    def make():
+        NE = max(int(log10(E0 / params.Emin) * params.NE_pd), params.NE_min)
+        return np.logspace(log(params.Emin), log(E0), NE, base=np.e)
+    return _memo_grid(("E", float(E0), params.Emin, params.NE_pd, params.NE_min), make)
 
 
 def temperature_grid(Tmin, Tmax):
     """NT and Tr exactly as nucl.py:473-477."""
-    NT = int(log10(Tmax / Tmin) * params.NT_pd)
-    return np.logspace(log10(Tmin), log10(Tmax), NT)
+    def make():
+        NT = int(log10(Tmax / Tmin) * params.NT_pd)
+        return np.logspace(log10(Tmin), log10(Tmax), NT)
+    return _memo_grid(("T", float(Tmin), float(Tmax), params.NT_pd), make)
 
 
 class _Arena(object):
@@ -377,7 +394,7 @@ class Engine(object):
         E = np.ascontiguousarray(np.broadcast_arrays(E, T)[0], dtype=np.float64).reshape(-1)
         T = np.ascontiguousarray(np.broadcast_to(T, E.shape), dtype=np.float64).reshape(-1)
         n = E.shape[0]
-        dE, dT = torch.from_numpy(E).to(self.device), torch.from_numpy(T).to(self.device)
+        dE, dT = torch.tensor(E, device=self.device), torch.tensor(T, device=self.device)
         out = torch.empty(n * 3, dtype=torch.float64, device=self.device)
         torch.cuda.current_stream(self.device).synchronize()
         self._check(self.lib.acro_total_rates(self.h, n, dE.data_ptr(), dT.data_ptr(), out.data_ptr(),

@@ -9,6 +9,7 @@ last bit of ``temperature(tau)`` ("bit-level grid conventio
 from math import log10
 from os import path
 import tarfile
+from time import monotonic
 
 import numpy as np
 from scipy.integrate import cumulative_simpson
@@ -22,8 +23,14 @@ def locate_data_file(filename):
     return path.join(pkg_dir, "data", filename)
 
 
+_SM_FILE = None
+
+
 def locate_sm_file():
-    return locate_data_file("sm.tar.gz")
+    global _SM_FILE
+    if _SM_FILE is None:
+        _SM_FILE = locate_data_file("sm.tar.gz")
+    return _SM_FILE
 
 
 class InputData(object):
@@ -61,15 +68,22 @@ def input_data_from_file(filename):
 
 
 _II_CACHE = {}
+_II_RECENT = {}    # filename -> (InputInterface, time of the last stat): a scan constructs thousands of models per second
 
 
 def shared_input_interface(filename=None):
-    """One InputInterface per input file and process (keyed on path, mtime and size)."""
+    """One InputInterface per input file and process (keyed on path, mtime and size; the file is re-examined at most
+    once per second)."""
     filename = locate_sm_file() if filename is None else filename
+    now = monotonic()
+    hit = _II_RECENT.get(filename)
+    if hit is not None and now - hit[1] < 1.0:
+        return hit[0]
     st = (path.abspath(filename), path.getmtime(filename), path.getsize(filename))
     ii = _II_CACHE.get(st)
     if ii is None:
         ii = _II_CACHE[st] = InputInterface(filename)
+    _II_RECENT[filename] = (ii, now)
     return ii
 
 
@@ -103,6 +117,7 @@ class InputInterface(object):
         self._sParamData = dict(pd.reshape(pd.size))
         self._sTempRange = None
         self._sSearch = {}      # per column: (ascending copy for searchsorted, descending flag)
+        self._sMemo = {}        # scalar interpolation results: the points of a grid scan repeat their arguments
         self._check_data()
 
     def _check_data(self):
@@ -134,9 +149,15 @@ class InputInterface(object):
         return n - np.searchsorted(xs, v, side="left") - 1
 
     def _interp_cosmo_data(self, val, xc, yc):
+        scalar = isinstance(val, (float, int)) or np.ndim(val) == 0
+        if scalar:
+            key = (xc, yc, float(val))
+            hit = self._sMemo.get(key)
+            if hit is not None:
+                return hit
         x = self._sCosmoDataLog[:, xc]
         y = self._sCosmoDataLog[:, yc]
-        if np.ndim(val) == 0:
+        if scalar:
             val_log = log10(val)
             ix = int(self._bracket(x, val_log, xc))
             n = x.shape[0]
@@ -144,7 +165,10 @@ class InputInterface(object):
                 raise ValueError("Interpolation error: Index out of range")
             m = (y[ix + 1] - y[ix]) / (x[ix + 1] - x[ix])
             b = y[ix] - m * x[ix]
-            return 10.**(m * val_log + b)
+            if len(self._sMemo) >= 65536:
+                self._sMemo.clear()
+            res = self._sMemo[key] = 10.**(m * val_log + b)
+            return res
         val_log = np.log10(np.asarray(val, dtype=np.float64))
         ix = self._bracket(x, val_log, xc)
         n = x.shape[0]

@@ -33,6 +33,22 @@ def _fsr_shape(E, EX):
     return np.where(ok, (1. / EX) * (alpha / pi) * (1. + (1. - xs)**2.) / xs * np.log((1. - xs) / y), 0.)
 
 
+_FSR_MEMO = {}
+
+
+def _fsr_columns(E_grid, EX):
+    """[NE,3] energy shape of the final-state-radiation source (photon column only); shared by the points of a scan."""
+    key = (float(EX), len(E_grid), float(E_grid[0]))
+    v = _FSR_MEMO.get(key)
+    if v is None:
+        if len(_FSR_MEMO) >= 8192:
+            _FSR_MEMO.clear()
+        ze = np.zeros(len(E_grid))
+        v = _FSR_MEMO[key] = np.column_stack([_fsr_shape(E_grid, EX), ze, ze])
+        v.setflags(write=False)
+    return v
+
+
 class AbstractModel(ABC):
 
     def __init__(self, e0, ii):
@@ -246,20 +262,23 @@ class DecayModel(AbstractModel):
         tau = rep([m._sTau for m in models])
         nd_all = rep([m._sN0a for m in models]) * n_gamma * sf_ratio**3. * np.exp(-delta_t / tau) * (hbar / tau)
         t_tmax = ii.time(np.array([max(m._sTrg) for m in models]))
+        # [sum NT, 3] source arrays of all points at once (same products as _source_arrays), sliced per point below
+        braa2, bree = rep([m._sBRaa * 2. for m in models]), rep([m._sBRee for m in models])
+        S0_all = np.empty((len(nd_all), 3))
+        S0_all[:, 0] = braa2 * nd_all
+        S0_all[:, 1] = S0_all[:, 2] = bree * nd_all
+        sc_all = np.zeros((len(nd_all), 3))
+        sc_all[:, 0] = S0_all[:, 1]
         specs, off = [], 0
         for k, m in enumerate(models):
-            nd = nd_all[off:off + nt[k]]
+            sl = slice(off, off + nt[k])
             off += nt[k]
             E_grid = energy_grid(m._sE0)
-            S0 = np.column_stack([m._sBRaa * 2. * nd, m._sBRee * nd, m._sBRee * nd])
             if m._sBRee == 0.:
-                specs.append(PointSpec(m._sE0, E_grid, Ts[k], S0, t_tmax[k]))
+                specs.append(PointSpec(m._sE0, E_grid, Ts[k], S0_all[sl], t_tmax[k]))
             else:
-                z = np.zeros_like(nd)
-                sc = np.column_stack([m._sBRee * nd, z, z])
-                ze = np.zeros(len(E_grid))
-                sc_E = np.column_stack([_fsr_shape(E_grid, m._sE0), ze, ze])
-                specs.append(PointSpec(m._sE0, E_grid, Ts[k], S0, t_tmax[k], _lib.SC_SEPARABLE, sc, sc_E))
+                specs.append(PointSpec(m._sE0, E_grid, Ts[k], S0_all[sl], t_tmax[k], _lib.SC_SEPARABLE, sc_all[sl],
+                                       _fsr_columns(E_grid, m._sE0)))
         return specs
 
 
