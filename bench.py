@@ -49,7 +49,7 @@ def workload_config(extra=None):
     c = {"workload": "cfg3 DecayModel mphi x tau 200x200 scan (examples/scan_decay_* ranges, no fast parameter); "
                      "step = one of 40 interleaved slices = 1000 scan points per GPU (160 below threshold)",
          "grid": [N_GRID, N_GRID], "points_per_step_per_gpu": N_GRID * N_GRID // N_SLICES, "NE_pd": prm.NE_pd,
-         "NT_pd": prm.NT_pd, "quad_order": prm.quad_order,
+         "NT_pd": prm.NT_pd, "quad_order": prm.quad_order, "wien_from": prm.wien_from,
          "l2": "inputs larger than L2: each step streams ~20 GB of kernel planes through HBM, no reuse between steps"}
     if extra:
         c.update(extra)
@@ -295,8 +295,9 @@ def main_gpu(args):
     solve_bytes = 5 * 8 * pairs       # the solve stage reads every K entry once (G, F, S0 are <1% of that)
     # DRAM traffic and executed-FP64 utilisation of the two kernel-builder kernels from the committed ncu captures of one
     # slice (profiles/r01_ncu_kernels_shared_kernel.txt, r01_ncu_kernels_wien_kernel.txt): bytes per slice, i.e. per launch pair
-    ncu = {"traffic_bytes_per_launch": 28.43e9 + 11.02e9, "algorithmic_bytes_per_launch": 5 * 8 * pairs / max(k_launches, 1),
-           "fp64_pipe_active_pct": {"kernels_shared_kernel": 38.4, "kernels_wien_kernel": 62.5},
+    ncu = {"traffic_bytes_per_launch": 21.55e9 + 9.43e9, "algorithmic_bytes_per_launch": 5 * 8 * pairs / max(k_launches, 1),
+           "fp64_pipe_active_pct": {"kernels_shared_kernel": 37.6, "kernels_wien_kernel": 54.2},
+           "issue_active_pct": {"kernels_shared_kernel": 39.9, "kernels_wien_kernel": 66.2},
            "source": "profiles/r01_ncu_kernels_shared_kernel.txt, profiles/r01_ncu_kernels_wien_kernel.txt"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -318,7 +319,8 @@ def main_gpu(args):
                          "share_of_step": stage_ms[1] / stage_ms.sum(), "ncu": ncu},
             "roofline_solve": {"kernel": "solve_pdi_kernel (stage ii+iii)", "bound": "hbm", "achieved": solve_bytes / (stage_ms[2] * 1e-3) / 1e9,
                                "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / (stage_ms[2] * 1e-3) / 1e9 / hbm_peak,
-                               "peak_source": hbm_peak_src, "traffic": None},
+                               "peak_source": hbm_peak_src, "traffic": 20.79e9,
+                               "traffic_source": "profiles/r01_ncu_solve_pdi_kernel.txt (bytes per slice)"},
             "stage_ms_per_step": {k: float(v / K) for k, v in zip(("rates", "kernels", "solve_pdi", "matrix"), stage_ms)},
             "clocks": clocks}
     if rank == 0:
