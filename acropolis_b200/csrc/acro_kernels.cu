@@ -1187,7 +1187,8 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
             const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT + (kTileScalars + 1) * kTT + (ACRO_FQ_LOGTAB ? 2 * kLogTab : 0) +
                                                  (size_t)kTT * kSharedThreads);
             const int64_t tri_max = (int64_t)b.ne_max * (b.ne_max + 1) / 2;
-            dim3 grid((unsigned)((tri_max + kSharedThreads - 1) / kSharedThreads), (unsigned)b.n_points);
+            const int64_t tiles_max = (tri_max + kSharedThreads - 1) / kSharedThreads;
+            dim3 grid((unsigned)((tiles_max + kTilesPerBlock - 1) / kTilesPerBlock), (unsigned)b.n_points);
             cudaError_t e = cudaSuccess;
             static bool attr_set = false;
             if (!attr_set) {

@@ -27,8 +27,14 @@ constexpr int kTileScalars = 8;   // per-temperature scalars of a tile kept in s
 #ifndef ACRO_TS_UNROLL
 #define ACRO_TS_UNROLL 1
 #endif
+#ifndef ACRO_TS_TILES
+#define ACRO_TS_TILES 4      // tiles of kSharedThreads pairs per block (one Bose table fill serves all of them)
+#endif
+#ifndef ACRO_TS_TOPX
+#define ACRO_TS_TOPX 50.0
+#endif
 #ifndef ACRO_TS_FISSION
-#define ACRO_TS_FISSION 2
+#define ACRO_TS_FISSION 2    // nodes evaluated together in the panel loop
 #endif
 #ifndef ACRO_TS_HC
 #define ACRO_TS_HC 2.0
@@ -55,7 +61,9 @@ constexpr int kMaxPan = ACRO_TS_MAXPAN;     // panels per point (12 fine + 12 co
 #ifndef ACRO_TS_THREADS
 #define ACRO_TS_THREADS 256
 #endif
+constexpr double kTopX = ACRO_TS_TOPX;       // top of the shared grid in units of the point's highest temperature
 constexpr int kSharedThreads = ACRO_TS_THREADS;
+constexpr int kTilesPerBlock = ACRO_TS_TILES;
 
 __constant__ double c_leg_modal[kPanN][kPanN];   // (2j+1)/2 * w_m * P_j(x_m): Legendre coefficients from nodal values
 __constant__ double c_leg_rec[kPanN][2];         // recurrence P_{j+1} = a_j t P_j - b_j P_{j-1}: a_j = (2j+1)/(j+1), b_j = j/(j+1)
@@ -69,7 +77,8 @@ struct SharedGrid {
 // the grid of one model point (uniform over the block and identical in both kernels)
 __device__ __forceinline__ SharedGrid shared_grid(double Tmin, double Tmax, double E_top, double Ephb_T_max) {
     SharedGrid g;
-    g.y_top = log(fmin(Ephb_T_max * Tmax, E_top));
+    // thermal photons beyond kTopX * Tmax carry < e^{-(kTopX - wien_from)} of any integral served here: no panels there
+    g.y_top = log(fmin(fmin(Ephb_T_max, kTopX) * Tmax, E_top));
     const double y_split = log(Tmin) - 1.0, y_want = log(Tmin) - 25.0;
     int nf = (int)ceil(g.y_top - y_split);
     nf = max(1, min(nf, kMaxPan - 1));
@@ -182,8 +191,8 @@ __device__ __forceinline__ int panel_of(const SharedGrid& g, double y) {   // pa
 template <int KIND>
 __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, double x_b0, const SharedGrid& g,
                                                 const double* __restrict__ sx, const double* __restrict__ six,
-                                                const double* __restrict__ sy, const double* __restrict__ sB, bool active,
-                                                double acc[kTT]) {
+                                                const double* __restrict__ sy, const double* __restrict__ sB, double* __restrict__ myW,
+                                                bool active, double acc[kTT]) {
 #pragma unroll
     for (int t = 0; t < kTT; ++t) acc[t] = 0.0;
     double a = active ? flog(fmax(x_a, 1e-300)) : g.y_top;
@@ -213,7 +222,8 @@ __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, 
         const bool full = inside && !is_part;
         const int base = pn * kPanN;
         if (!__any_sync(0xffffffffu, inside)) continue;
-        if (__any_sync(0xffffffffu, is_part)) {
+        const bool any_part = __any_sync(0xffffffffu, is_part), any_full = __any_sync(0xffffffffu, full);
+        if (any_part) {
             double nu[kPanN];
 #pragma unroll
             for (int m = 0; m < kPanN; ++m) nu[m] = 0.0;
@@ -222,58 +232,28 @@ __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, 
                 const double hi_y = (part_hi && pn == p_last) ? bb : lo + h;
                 partial_panel<KIND>(c, x_a, lna, lo_y, hi_y, lo, h, layer ? bb : hi_y + 2.0, nu);
             }
+            // through the thread's shared-memory column, so that ONE accumulation block below serves the lanes that are
+            // partial in this panel and the lanes that are full (a warp usually has both near the lower limits)
 #pragma unroll
-            for (int m = 0; m < kPanN; ++m) {
-                const double* __restrict__ Bk = sB + (size_t)(base + m) * kTT;
-                const double v = nu[m];
-#pragma unroll
-                for (int t = 0; t < kTT; ++t) acc[t] = fma(v, Bk[t], acc[t]);
-            }
+            for (int m = 0; m < kPanN; ++m) myW[m * kSharedThreads] = nu[m];
         }
-        if (__any_sync(0xffffffffu, full)) {
-#if ACRO_TS_FISSION
-            // Node values first, accumulation second: the kPanN evaluations are independent dependency chains that the
-            // scheduler can interleave (two warps per scheduler cannot hide one chain behind another warp's).  Branch-free:
-            // lanes without this panel carry weight 0 and finite arguments.
-            const double wscale = full ? 0.5 * h : 0.0;
-            constexpr int kGroup = ACRO_TS_FISSION;     // nodes evaluated together
-            static_assert(kPanN % kGroup == 0, "node group must divide the panel");
+        // Node values first, accumulation second, kGroup nodes at a time: the evaluations are independent dependency
+        // chains that the scheduler interleaves (two warps per scheduler cannot hide one chain behind another warp's);
+        // more than two outgrow the L0 instruction cache.  Branch-free: lanes without this panel carry weight 0 and
+        // finite arguments.
+        const double wscale = full ? 0.5 * h : 0.0;
+        constexpr int kGroup = ACRO_TS_FISSION;
+        static_assert(kPanN % kGroup == 0, "node group must divide the panel");
 #pragma unroll 1
-            for (int m0 = 0; m0 < kPanN; m0 += kGroup) {
+        for (int m0 = 0; m0 < kPanN; m0 += kGroup) {
             double fv[kGroup];
+            if (any_full) {
 #pragma unroll
-            for (int mm = 0; mm < kGroup; ++mm) {
-                const int m = m0 + mm;
-                const int k = base + m;
-                const double x = sx[k];
-                double f;
-                if (KIND == KIND_IC_PHOTON) {
-                    const double q = x_a * six[k];
-                    const double omq = 1.0 - q;
-                    f = fma(2.0 * q, lna - sy[k], fma(fma(2.0, q, 1.0), omq, c.c9 * omq));
-                } else if (KIND == KIND_IC_ELECTRON) {
-                    f = integrand_core<KIND_IC_ELECTRON>(c, x, x_a, 0.0, false);
-                } else {   // the table holds x^2/(e^{x/T}-1); the pair-creation integrand carries x^1
-                    f = integrand_core<KIND_PC_ELECTRON>(c, x, x_a, 0.0, false) * six[k];
-                }
-                fv[mm] = full ? f * (c_glw[gl_offset(kPanN) + m] * wscale) : 0.0;
-            }
-#pragma unroll
-            for (int mm = 0; mm < kGroup; ++mm) {
-                const double* __restrict__ Bk = sB + (size_t)(base + m0 + mm) * kTT;
-                const double f = fv[mm];
-#pragma unroll
-                for (int t = 0; t < kTT; ++t) acc[t] = fma(f, Bk[t], acc[t]);
-            }
-            }
-#else
-            const double wscale = 0.5 * h;
-            ACRO_UNROLL(ACRO_TS_UNROLL)
-            for (int m = 0; m < kPanN; ++m) {
-                const int k = base + m;
-                double f = 0.0;
-                if (full) {
+                for (int mm = 0; mm < kGroup; ++mm) {
+                    const int m = m0 + mm;
+                    const int k = base + m;
                     const double x = sx[k];
+                    double f;
                     if (KIND == KIND_IC_PHOTON) {
                         const double q = x_a * six[k];
                         const double omq = 1.0 - q;
@@ -283,13 +263,23 @@ __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, 
                     } else {   // the table holds x^2/(e^{x/T}-1); the pair-creation integrand carries x^1
                         f = integrand_core<KIND_PC_ELECTRON>(c, x, x_a, 0.0, false) * six[k];
                     }
-                    f *= c_glw[gl_offset(kPanN) + m] * wscale;
+                    fv[mm] = full ? f * (c_glw[gl_offset(kPanN) + m] * wscale) : 0.0;
                 }
-                const double* __restrict__ Bk = sB + (size_t)k * kTT;
+            } else {
+#pragma unroll
+                for (int mm = 0; mm < kGroup; ++mm) fv[mm] = 0.0;
+            }
+            if (any_part) {
+#pragma unroll
+                for (int mm = 0; mm < kGroup; ++mm) fv[mm] += myW[(m0 + mm) * kSharedThreads];
+            }
+#pragma unroll
+            for (int mm = 0; mm < kGroup; ++mm) {
+                const double* __restrict__ Bk = sB + (size_t)(base + m0 + mm) * kTT;
+                const double f = fv[mm];
 #pragma unroll
                 for (int t = 0; t < kTT; ++t) acc[t] = fma(f, Bk[t], acc[t]);
             }
-#endif
         }
     }
 }
@@ -304,8 +294,9 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
     const int pt = blockIdx.y;
     const int ne = b.pt_ne[pt], nt = b.pt_nt[pt], s0 = b.pt_sys_off[pt];
     const int64_t tri = (int64_t)ne * (ne + 1) / 2;
-    const int64_t loc0 = (int64_t)blockIdx.x * kSharedThreads;
-    if (loc0 >= tri) return;
+    const int tiles = (int)((tri + kSharedThreads - 1) / kSharedThreads);
+    const int tile0 = blockIdx.x * kTilesPerBlock, tile_end = min(tiles, tile0 + kTilesPerBlock);
+    if (tile0 >= tiles) return;
     const double* eg = b.e_grid + b.pt_e_off[pt];
     const double Tmin = b.sys_T[s0], Tmax = b.sys_T[s0 + nt - 1];
     const SharedGrid g = shared_grid(Tmin, Tmax, eg[ne - 1], p.Ephb_T_max);
@@ -330,50 +321,6 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
         const double x = fexp(y);
         sy[k] = y; sx[k] = x; six[k] = frcp(x);
     }
-    // this thread's pair
-    const int64_t loc = loc0 + threadIdx.x;
-    const bool active = loc < tri;
-    int i = 0, j = 0;
-    if (active) {
-        const double tn = 2.0 * ne + 1.0;
-        i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
-        i = max(0, min(i, ne - 1));
-        while (i > 0 && tri_row_off(i, ne) > loc) --i;
-        while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
-        j = i + (int)(loc - tri_row_off(i, ne));
-    }
-    const double E = eg[i], Ep = eg[j];
-    PairConst c;
-    c.E = E; c.Ep = Ep; c.dE = Ep - E;
-    {
-        const double r = E / fmax(c.dE, 1e-300);
-        c.c9 = r * r / (2.0 + 2.0 * r);
-        c.c10 = 0.25 * kMe2 / Ep;
-        c.i2Ep = 0.5 / Ep;
-    }
-#if ACRO_FQ_LOGTAB
-    c.lt = s_lt;
-#endif
-    const PairLimits L = pair_limits(E, Ep);
-    const double x_bot = exp(g.y_bot);
-    const int64_t np = b.n_pairs_total;
-    // pair-only parts of the closed forms (cascade.py:383-402, 550-558, 621-639)
-    const double a2 = kAlpha * kAlpha;
-    const double pre_ic = 2.0 * kPi * a2 / (Ep * Ep);
-    const double pre_pc = 0.25 * kPi * a2 * kMe2 / (Ep * Ep * Ep);
-    const double rr = E / Ep, gg_shape = 1.0 - rr + rr * rr;
-    const double pp_pair = 1112.0 / (10125.0 * kPi) * (a2 * a2) / ((kMe2 * kMe2) * (kMe2 * kMe2)) * 8.0 * (kPi2 * kPi2) / 63.0 *
-                           (Ep * Ep) * (gg_shape * gg_shape);
-    const double compton_g = kernel_compton_core(E, Ep, 1.0);               // per unit electron density
-    const double compton_e = kernel_compton_core(Ep + kMe - E, Ep, 1.0);
-    const double bh_pair = (L.xa9 > 0.0) ? bh_dsdE_Z2(E, Ep) : 0.0;         // same condition E' >= E + me
-
-    // the lowest grid node is below every lower limit that matters (shared_regime(), second clause)
-    const bool deep = x_bot <= 2e-11 * Tmin;
-    const bool has9 = active && L.xa9 > 0.0, has10 = active && L.xa10 > 0.0, has11 = active && L.xb11 > L.xa11;
-    const bool reg9 = has9 && (deep || L.xa9 >= x_bot), reg10 = has10 && (deep || L.xa10 >= x_bot),
-               reg11 = has11 && (deep || L.xa11 >= x_bot);
-
     for (int t0 = 0; t0 < nt; t0 += kTT) {
         __syncthreads();
         if (threadIdx.x < kTT) {
@@ -402,8 +349,54 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
             sB[idx] = v;
         }
         __syncthreads();
-        double acc[kTT];
         const int ntile = min(kTT, nt - t0);
+        // the block walks over kTilesPerBlock tiles of 256 pairs: the node tables and the Bose table above are per point and
+        // temperature tile, not per pair (filling them once per 256 pairs was 17 % of the instructions)
+        for (int tile = tile0; tile < tile_end; ++tile) {
+        // this thread's pair
+        const int64_t loc = (int64_t)tile * kSharedThreads + threadIdx.x;
+        const bool active = loc < tri;
+        int i = 0, j = 0;
+        if (active) {
+            const double tn = 2.0 * ne + 1.0;
+            i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+            i = max(0, min(i, ne - 1));
+            while (i > 0 && tri_row_off(i, ne) > loc) --i;
+            while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
+            j = i + (int)(loc - tri_row_off(i, ne));
+        }
+        const double E = eg[i], Ep = eg[j];
+        PairConst c;
+        c.E = E; c.Ep = Ep; c.dE = Ep - E;
+        {
+            const double r = E / fmax(c.dE, 1e-300);
+            c.c9 = r * r / (2.0 + 2.0 * r);
+            c.c10 = 0.25 * kMe2 / Ep;
+            c.i2Ep = 0.5 / Ep;
+        }
+    #if ACRO_FQ_LOGTAB
+        c.lt = s_lt;
+    #endif
+        const PairLimits L = pair_limits(E, Ep);
+        const double x_bot = exp(g.y_bot);
+        const int64_t np = b.n_pairs_total;
+        // pair-only parts of the closed forms (cascade.py:383-402, 550-558, 621-639)
+        const double a2 = kAlpha * kAlpha;
+        const double pre_ic = 2.0 * kPi * a2 / (Ep * Ep);
+        const double pre_pc = 0.25 * kPi * a2 * kMe2 / (Ep * Ep * Ep);
+        const double rr = E / Ep, gg_shape = 1.0 - rr + rr * rr;
+        const double pp_pair = 1112.0 / (10125.0 * kPi) * (a2 * a2) / ((kMe2 * kMe2) * (kMe2 * kMe2)) * 8.0 * (kPi2 * kPi2) / 63.0 *
+                               (Ep * Ep) * (gg_shape * gg_shape);
+        const double compton_g = kernel_compton_core(E, Ep, 1.0);               // per unit electron density
+        const double compton_e = kernel_compton_core(Ep + kMe - E, Ep, 1.0);
+        const double bh_pair = (L.xa9 > 0.0) ? bh_dsdE_Z2(E, Ep) : 0.0;         // same condition E' >= E + me
+
+        // the lowest grid node is below every lower limit that matters (shared_regime(), second clause)
+        const bool deep = x_bot <= 2e-11 * Tmin;
+        const bool has9 = active && L.xa9 > 0.0, has10 = active && L.xa10 > 0.0, has11 = active && L.xb11 > L.xa11;
+        const bool reg9 = has9 && (deep || L.xa9 >= x_bot), reg10 = has10 && (deep || L.xa10 >= x_bot),
+                   reg11 = has11 && (deep || L.xa11 >= x_bot);
+        double acc[kTT];
         // a pair takes part in the shared integrals of this tile only if its lower limit is off the Wien tail for the
         // tile's highest temperature
         const double xa_max = sT[5 * kTT + ntile - 1];
@@ -415,7 +408,7 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
         // ---- e -> gamma (plane 1)
         {
             const bool act = has9 && L.xb9 > L.xa9 && L.xa9 <= xa_max;
-            shared_integral<KIND_IC_PHOTON>(c, L.xa9, L.xb9, g, sx, six, sy, sB, act, acc);
+            shared_integral<KIND_IC_PHOTON>(c, L.xa9, L.xb9, g, sx, six, sy, sB, myA, act, acc);
 #pragma unroll
             for (int t = 0; t < kTT; ++t) myA[t * kSharedThreads] = acc[t];
             if (active) {
@@ -429,7 +422,7 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
         // ---- e -> e (plane 4)
         {
             const bool act = has10 && L.xb10 > L.xa10 && L.xa10 <= xa_max;
-            shared_integral<KIND_IC_ELECTRON>(c, L.xa10, L.xb10, g, sx, six, sy, sB, act, acc);
+            shared_integral<KIND_IC_ELECTRON>(c, L.xa10, L.xb10, g, sx, six, sy, sB, myA, act, acc);
 #pragma unroll
             for (int t = 0; t < kTT; ++t) myA[t * kSharedThreads] = acc[t];
             if (active) {
@@ -443,7 +436,7 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
         // ---- gamma -> e-/e+ (planes 2, 3) and gamma -> gamma (plane 0)
         {
             const bool act = has11 && L.xa11 <= xa_max && !(Ep < sT[6 * kTT + ntile - 1]);
-            shared_integral<KIND_PC_ELECTRON>(c, L.xa11, L.xb11, g, sx, six, sy, sB, act, acc);
+            shared_integral<KIND_PC_ELECTRON>(c, L.xa11, L.xb11, g, sx, six, sy, sB, myA, act, acc);
 #pragma unroll
             for (int t = 0; t < kTT; ++t) myA[t * kSharedThreads] = acc[t];
             if (active) {
@@ -462,6 +455,7 @@ __global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_k
                 }
             }
         }
+        }   // tiles
     }
 }
 
