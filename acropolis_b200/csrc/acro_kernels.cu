@@ -1202,12 +1202,13 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
         }
     } else {
         if (p.kernel_mode == ACRO_KERNELS_FAST) {   // the production kernel builder (acro_tshared.cuh): all five planes
-            const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT + (kTileScalars + 1) * kTT + (ACRO_FQ_LOGTAB ? 2 * kLogTab : 0) +
-                                                 (size_t)kTT * kSharedThreads);
             const int64_t tri_max = (int64_t)b.ne_max * (b.ne_max + 1) / 2;
             const int64_t tiles_max = (tri_max + kSharedThreads - 1) / kSharedThreads;
             dim3 grid((unsigned)((tiles_max + kTilesPerBlock - 1) / kTilesPerBlock), (unsigned)b.n_points);
+            const size_t smem_tables = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT +
+                                                         (kTileScalars + 1) * kTT + (ACRO_FQ_LOGTAB ? 2 * kLogTab : 0));
             cudaError_t e = cudaSuccess;
+            const size_t smem = smem_tables + sizeof(double) * (size_t)kTT * kSharedThreads;
             static bool attr_set = false;
             if (!attr_set) {
                 e = cudaFuncSetAttribute(kernels_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
