@@ -283,6 +283,23 @@ def test_c_abi_host_entry(gpu_engine, results):
     assert b"ne_max" in gpu_engine.lib.acro_last_error(gpu_engine.h)
 
 
+def test_wien_from_parameter(gpu_engine):
+    """acro_params_t.wien_from: rejected outside [e, e^2] with a message; the two ends agree within the documented 1e-7;
+    the stage split timer reports both kernels of the production builder."""
+    z = golden("decay_big.npz")
+    sp = spec_from_golden(z)
+    with wien_from(10.0):
+        with pytest.raises(RuntimeError, match="wien_from"):
+            gpu_engine.kernels_of(sp, 0)
+    K2, _ = gpu_engine.kernels_of(sp, 19)          # default again (a rejected parameter set leaves the old one active)
+    ms = gpu_engine.kernel_split_ms()
+    assert ms.shape == (2,) and (ms > 0).all()
+    with wien_from(E1):
+        K1, _ = gpu_engine.kernels_of(sp, 19)
+    assert np.array_equal(K1 != 0, K2 != 0)
+    assert relerr(K2, K1) < 1e-7
+
+
 def test_fast_kernels_match_plain_gauss_legendre(gpu_engine):
     """Production evaluation of the thermal integrals (Gauss-Laguerre on the Wien tail, reduced integrands, Q/2 rule on
     short ranges) against the plain Gauss-Legendre evaluation at Q=96 with the reference's F/G range tests."""
