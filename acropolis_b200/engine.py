@@ -138,8 +138,6 @@ class Engine(object):
         self._arena = _Arena(device)
         self._ws = None
         self._params_key = None
-        self.last_stage_ms = np.zeros(4)
-        self.stage_ms_total = np.zeros(4)
 
     def __del__(self):
         try:
@@ -311,8 +309,12 @@ class Engine(object):
                 outs["F"] = torch.empty(NF * 3, dtype=torch.float64, device=dev)
             need = int(self.lib.acro_workspace_bytes(self.h, C.byref(b)))
             if self._ws is None or self._ws.numel() < need:
+                # growing means cudaMalloc, and that waits for everything in flight (measured: 14-37 ms in the middle of a
+                # pipelined scan whose later points are larger): grow with 50 % headroom so that it happens once or twice
+                free, _ = torch.cuda.mem_get_info(dev)
+                have = self._ws.numel() if self._ws is not None else 0
                 self._ws = None
-                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+                self._ws = torch.empty(int(min(max(need, 1.5 * need), max(need, 0.8 * (free + have)))), dtype=torch.uint8, device=dev)
         o = _lib.Out()
         for k, t in outs.items():
             setattr(o, k, t.data_ptr())
@@ -361,11 +363,7 @@ class Engine(object):
         return self._arenas[self._arena_i]
 
     def _collect(self, pnd, res):
-        pnd["ev"].synchronize()
-        ms = (C.c_float * 4)()
-        if self.lib.acro_last_stage_ms(self.h, C.byref(ms)) == 0:
-            self.last_stage_ms = np.array(list(ms), dtype=np.float64)
-            self.stage_ms_total += self.last_stage_ms
+        pnd["ev"].synchronize()     # this chunk's own event only: later chunks keep the GPU busy meanwhile
         cnt = pnd["cnt"]
         shapes = dict(Yf=(cnt["n_points"], 9, 3), mpdi=(cnt["n_points"], 9, 9), mdcy=(cnt["n_points"], 9, 9),
                       status=(cnt["n_points"],), pdi=(cnt["n_systems"], _lib.NR), G=(-1,), F=(-1,))

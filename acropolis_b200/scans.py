@@ -146,12 +146,16 @@ def run_models(models, devices=None, want_matp=False):
     return (Yf, matp) if want_matp else Yf
 
 
-def run_points(model, param_sets, devices=None, group=256):
+def run_points(model, param_sets, devices=None, group=2048, first_group=384, growth=8):
     """Rows ``[sorted params..., 9 mean, 9 high, 9 low]`` for an arbitrary list of parameter dicts of one model class
     (or ``functools.partial``): the batched form of ``BufferedScanner._run_single`` (reference scans.py:110-124).
     Builds the models, stages their grids and source arrays, runs the CUDA path and reads the abundances back.  On one
-    device the list is processed in groups of `group` points: while the GPU works on one group the host constructs the
-    models and source arrays of the next."""
+    device the list is processed in groups: while the GPU works on one group the host constructs the models and source
+    arrays of the next.  The groups grow geometrically (`first_group`, then x`growth` up to `group`).  Measured on a
+    1000-point slice of the benchmark scan (tools/gpu_e2e_timeline.py; host ~12 us per point, GPU ~95 us): every extra
+    launch costs ~1 ms of GPU time (tails of the longest blocks) and the GPU idles while the host prepares a group that is
+    more than ~8x the previous one, so two groups (384 + rest: 92 ms wall for 84 ms of GPU work) beat both one group
+    (96 ms: nothing overlaps) and 32/128/512/rest (95 ms)."""
     import torch
     if devices is None:
         dist = _dist_world()
@@ -173,32 +177,36 @@ def run_points(model, param_sets, devices=None, group=256):
             rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
 
     ncol = 3
-    # group boundaries: a small first group gets the GPU going early, then `group` points at a time
-    bounds, g0 = [], 0
-    while g0 < N:
-        g1 = min(N, g0 + (max(32, group // 4) if not bounds else group))
-        bounds.append((g0, g1))
-        g0 = g1
-    for g0, g1 in bounds:
-        idx, todo = [], []
-        for i in range(g0, g1):
-            m = model(**param_sets[i])
-            ncol = m._sII.bbn_abundances().shape[1]
-            if m.is_trivial():
-                Y = m._squeeze_decays(m._sII.bbn_abundances())
-                p = param_sets[i]
-                rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
-            else:
-                if eng is None:
-                    eng = Engine.get(m._sII, devices[0])
-                    eng.last_h2d_bytes = eng.last_d2h_bytes = 0
-                idx.append(i)
-                todo.append(m)
+    # groups are counted in points that NEED the GPU (points below all thresholds are answered on the spot and a scan
+    # may start with hundreds of them); a small first group gets the GPU going early, then `group` points at a time
+    idx, todo, first, target = [], [], True, min(group, first_group)
+
+    def flush():
+        nonlocal idx, todo, first
         if todo:
             specs = type(todo[0]).point_specs(todo) if len({type(m) for m in todo}) == 1 else [m.point_spec() for m in todo]
             in_flight.append((idx, eng.submit(specs, want=("Yf", "status"))))
+            idx, todo, first = [], [], False
         while len(in_flight) > 2:
             finish(in_flight.pop(0))
+
+    for i in range(N):
+        m = model(**param_sets[i])
+        ncol = m._sII.bbn_abundances().shape[1]
+        if m.is_trivial():
+            Y = m._squeeze_decays(m._sII.bbn_abundances())
+            p = param_sets[i]
+            rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
+            continue
+        if eng is None:
+            eng = Engine.get(m._sII, devices[0])
+            eng.last_h2d_bytes = eng.last_d2h_bytes = 0
+        idx.append(i)
+        todo.append(m)
+        if len(todo) >= target:
+            flush()
+            target = min(group, growth * target)     # see the docstring
+    flush()
     for entry in in_flight:
         finish(entry)
     return np.array(rows)

@@ -44,7 +44,7 @@ for name in names:
     line = "%-24s NE=%3d NT=%3d %.3fs st=%d  G %.1e  F %.1e  pdi %.1e  mpdi %.1e  mdcy %.1e  Yf %.1e" % (
         name, NE, NT, dt, out["status"][0], rel(Gd, z["G"]), rel(Fd, z["F"]), rel(out["pdi"], z["pdi"], 1e-100),
         rel(out["mpdi"][0], z["mpdi"], 1e-100), rel(out["mdcy"][0], z["mdcy"], 1e-100), rel(out["Yf"][0], z["Yf"], 1e-30))
-    print(line, " stage_ms", np.round(eng.last_stage_ms, 3))
+    print(line, " stage_ms", np.round(eng.stage_ms(), 3))
     for it in z["k_at"]:
         K, Gk = eng.kernels_of(sp, int(it))
         Kr = z["K_it%d" % it]
