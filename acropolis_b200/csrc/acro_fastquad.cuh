@@ -4,10 +4,12 @@
 // version in acro_kernels.cu (kernel_mode = ACRO_KERNELS_PLAIN_GL, kept as the in-library cross-check); what changes
 // is how they are evaluated:
 //
-//  * STEEP regime  x_a/T > e  and  (x_b - x_a)/T >= 45  (the lower limit sits on the Wien tail of the thermal photons):
+//  * STEEP regime  x_a/T > e  and  (x_b - x_a)/T >= 32  (the lower limit sits on the Wien tail of the thermal photons):
 //    with s = (x - x_a)/T the integral is  T e^{-x_a/T}/pi^2 * int_0^inf e^{-s} g(s) ds,  g smooth on the scale x_a/T > e,
-//    so a 24-point Gauss-Laguerre rule is exact to < 1e-10 (tools/proto: 4e-11 worst) -- and needs NO exponential per
-//    node (e^{-s_k} are constants).  Nodes beyond x_b (weight < e^-45) are masked.
+//    so a Gauss-Laguerre rule of 24 ... 4 nodes (by x_a/T) is exact to < 4e-10 -- and needs NO exponential per node
+//    (e^{-s_k} are constants).  Nodes beyond x_b (weight < e^-32) are masked.  Shorter spans: GL-32 in s.
+//  * log and exp: a 128-entry table-driven log (flog_tab) and Estrin-evaluated polynomials (ACRO_FQ_LOGTAB, ACRO_FQ_ESTRIN;
+//    0 selects the atanh-series log / Horner forms they replaced: same results to 2e-16, 5 % slower kernels).
 //  * otherwise the Q-point Gauss-Legendre rule in log(eps_bar) as before, but with the integrands reduced
 //    algebraically (q = x_a/x for the photon kernel so that log q = log x_a - y; Gamma*q = A/B with A + B = E' for
 //    the electron kernel; one shared reciprocal for the pair-creation function), division-free reciprocals and a
@@ -21,9 +23,6 @@
 #endif
 #ifndef ACRO_FQ_ESTRIN
 #define ACRO_FQ_ESTRIN 1
-#endif
-#ifndef ACRO_FQ_LAGSHIFT
-#define ACRO_FQ_LAGSHIFT 0
 #endif
 #ifndef ACRO_FQ_LOGTAB
 #define ACRO_FQ_LOGTAB 1
@@ -39,7 +38,7 @@ __constant__ double c_lag_s[70];
 __constant__ double c_lag_w[70];
 __constant__ double c_lag_es[70];
 
-__constant__ double c_half_range = 8.0;           // log-range [e-folds] up to which Q/2 nodes are used (a9, a11 only)
+constexpr double kHalfRange = 8.0;              // log-range [e-folds] up to which Q/2 nodes are used (a9, a11 only)
 constexpr double kSteepX = 2.718281828459045;   // x_a/T above which the Laguerre form is used (u_a > 1)
 constexpr double kSteepSpan = 32.0;             // and the span (x_b - x_a)/T must exceed this (truncation e^-32)
 
@@ -210,20 +209,12 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
         //   va in (e, e^1.5]: 24   (e^1.5, e^2]: 16   (e^2, e^2.5]: 12   (e^2.5, e^3]: 8   (e^3, e^4]: 6   > e^4: 4
         const double Ea = fexp(-va);
         int n, off;
-#if ACRO_FQ_LAGSHIFT   // experiment: one order lower in every band
-        if (va > 20.085536923187668) { n = 4; off = 0; }
-        else if (va > 12.182493960703473) { n = 6; off = 4; }
-        else if (va > 7.38905609893065) { n = 8; off = 10; }
-        else if (va > 4.4816890703380645) { n = 12; off = 18; }
-        else { n = 16; off = 30; }
-#else
         if (va > 54.598150033144236) { n = 4; off = 0; }
         else if (va > 20.085536923187668) { n = 6; off = 4; }
         else if (va > 12.182493960703473) { n = 8; off = 10; }
         else if (va > 7.38905609893065) { n = 12; off = 18; }
         else if (va > 4.4816890703380645) { n = 16; off = 30; }
         else { n = 24; off = 46; }
-#endif
         double sum = 0.0;
 #pragma unroll 1
         for (int kk = 0; kk < n; ++kk) {
@@ -260,7 +251,7 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
     // node count by the width of the log-range: the Q-point rule, or Q/2 points when the range is short.  Measured on a
     // 168-point slice sample against Q=96: with ranges <= 8 e-folds at Q/2 = 32 the photon (a9) and pair (a11) kernels
     // stay within 1e-9; the electron kernel (a10) does not (2e-7 already at 4.5 e-folds) and always uses Q.
-    const bool half = (Q >= 32) && (KIND != KIND_IC_ELECTRON) && (b - a <= c_half_range);
+    const bool half = (Q >= 32) && (KIND != KIND_IC_ELECTRON) && (b - a <= kHalfRange);
     const int n = half ? Q / 2 : Q;
     const double* gx = c_glx + (half ? gl_offset(Q / 2 < 8 ? 8 : Q / 2) : gl_offset(Q));
     const double* gw = c_glw + (half ? gl_offset(Q / 2 < 8 ? 8 : Q / 2) : gl_offset(Q));

@@ -2,8 +2,11 @@
 //
 //   rates_kernel        thread per (system, E_i)        G[3,NE]: closed forms + rates.db bilinear interpolation
 //   direct_rates_kernel warp per out-of-table (E,T)     the two 2-D rate integrals the reference does with dblquad
-//   kernels_kernel      thread per (system, E_i, E_j>=i) five K planes: closed forms + three Planck-weighted
-//                                                       fixed-order Gauss-Legendre integrals in log(eps_bar)
+//   kernels_shared_kernel / kernels_wien_kernel         the production kernel builder (acro_tshared.cuh): five K planes,
+//                                                       closed forms + three Planck-weighted integrals on a
+//                                                       temperature-shared grid / Gauss-Laguerre on the Wien tail
+//   kernels_kernel      thread per (system, E_i, E_j>=i) cross-check modes: fixed-order Gauss-Legendre in log(eps_bar)
+//                                                       per (E,E',T) (PLAIN_GL with the reference's F/G, PER_T reduced)
 //   solve_pdi_kernel    warp per system                 back-substitution of the 3-species cascade equation,
 //                                                       fused with the 17 sigma(E)*F(E) rate integrals
 //   matrix_kernel       warp per point                  exact piecewise T-integral, 9x9 expm, decay matrices, Yf
@@ -22,7 +25,7 @@
 namespace acro {
 
 // ------------------------------------------------------------------------------------------------------------
-// Gauss-Legendre tables in constant memory: orders 8, 16, 32, 64, 96, 128 packed back to back.
+// Gauss-Legendre tables in constant memory: orders 8, 16, 32, 64, 96, 128, 12, 10 packed back to back.
 // ------------------------------------------------------------------------------------------------------------
 // cross-section tables of sigma_rt (filled by upload_quadrature_tables)
 __constant__ double c_sig[ACRO_NR][4];    // generic reactions: {log(N Q^p1), p2, p3, Q}
@@ -1180,17 +1183,10 @@ cudaError_t launch_direct_rates(const DeviceTables& t, const acro_params_t& p, d
     return cudaGetLastError();
 }
 
-cudaError_t set_half_range(double v) { return cudaMemcpyToSymbol(c_half_range, &v, sizeof(double)); }
-
 cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const acro_params_t& p, double* Kws,
                            cudaStream_t st, LaunchCounters& lc) {
     lc.split_valid = false;
     if (b.n_pairs_total == 0) return cudaSuccess;
-    if (const char* hr = getenv("ACRO_HALF_RANGE")) {   // experiment knob (A/B runs only)
-        static double last = -1.0;
-        const double v = atof(hr);
-        if (v != last) { cudaMemcpyToSymbolAsync(c_half_range, &v, sizeof(double), 0, cudaMemcpyHostToDevice, st); last = v; }
-    }
     const int64_t blocks = (b.n_pairs_total + 127) / 128;
     const unsigned g = (unsigned)blocks;
     if (p.kernel_mode == ACRO_KERNELS_PLAIN_GL) {

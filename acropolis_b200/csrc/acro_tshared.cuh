@@ -1,69 +1,74 @@
-// acro_tshared.cuh -- temperature-shared evaluation of the three thermal kernel integrals.
+// acro_tshared.cuh -- the production kernel builder (kernel_mode = ACRO_KERNELS_FAST): temperature-shared evaluation of
+// the three thermal kernel integrals (kernels_shared_kernel) plus the per-temperature Wien-tail kernel (kernels_wien_kernel).
 //
 // In   K(E,E',T) ~ int f(E,E',x) * x^p / (e^{x/T} - 1) dlog x   the factor f (the functions F, G of cascade.py:29-80) does
 // not depend on T and the Bose factor does not depend on (E,E').  For all temperatures of one model point whose lower
-// limit is not on the Wien tail (x_a <= e T) and whose upper limit is the thermal cut-off (200 T < x_b0), the integral is
-// therefore evaluated on ONE panel grid in y = log x that is shared by every pair and every temperature of the point:
+// limit satisfies x_a <= wien_from * T (acro_params_t.wien_from, e..e^2) the integral is therefore evaluated on ONE panel
+// grid in y = log x that is shared by every pair and every temperature of the point:
 //
-//   * panels of 12 Gauss-Legendre nodes (16 gives the same answers to 5e-10 and costs 14 % more): width 1 e-fold from y_top = log(min(200 Tmax, E0)) down to log(Tmin) - 1 (where
-//     some temperature still sees the Planck roll-off), width 2 below, down to log(Tmin) - 25 (what lies below
-//     contributes < 2e-11);
-//   * per temperature tile, the Bose factors at the grid nodes (and their Legendre coefficients per panel) are staged in
-//     SHARED MEMORY once per thread block -- the "thermal-photon grid" of BASELINE.json:north_star;
-//   * each thread owns one (E,E') pair: f is evaluated once per node and accumulated into TT temperature sums with one
+//   * panels of 12 Gauss-Legendre nodes: 1 e-fold wide from y_top = log(min(50 Tmax, E0)) down to log(Tmin) - 1 (where
+//     some temperature still sees the Planck roll-off), 2 e-folds wide below, down to log(Tmin) - 25 (what lies below
+//     contributes < 2e-11; what lies above 50 Tmax < 3e-19);
+//   * per temperature tile the Bose factors at the grid nodes are staged in SHARED MEMORY once per thread block and serve
+//     kTilesPerBlock tiles of 256 pairs -- the "thermal-photon grid" of BASELINE.json:north_star;
+//   * each thread owns one (E,E') pair: f is evaluated once per node and accumulated into kTT temperature sums with one
 //     FMA each; the panel that contains the lower limit is integrated on its own nodes against the Legendre expansion of
 //     the Bose factor (exact for what the panel rule itself resolves), and so is the panel that contains the upper limit
 //     when that is the kinematic one (x_b0 < 200 T); the thermal cut-off 200 T is applied as zeros in the Bose table.
 //
-// Measured against the converged per-(pair,T) rule (tools/proto/tshared_proto.py): <= 1e-11 for x_a <= e T.
-// The raw integrals are written into the K planes (eg, ee, ge+ slots); kernels_kernel<.,FAST> then picks them up for the
-// (pair,T) combinations that satisfy shared_regime() and evaluates the rest itself (Gauss-Laguerre / Gauss-Legendre).
+// kernels_shared_kernel writes all five planes (closed forms included); kernels_wien_kernel then overwrites / adds the
+// (pair, T) combinations beyond wien_from * T with its own Gauss-Laguerre rule (acro_fastquad.cuh).  Both evaluate the
+// regime predicates with the same expressions on the same numbers.
+//
+// Tuning constants (each is a -D macro so that tools/gpu_ab_variants.py can time a variant library; values = measured best
+// on the 840-point benchmark slice):
+//   ACRO_TS_TT      40   temperatures per tile = accumulators per thread.  One 256-thread block per SM (248 registers) beats
+//                        20 per tile with two blocks by 18 %: f is evaluated once instead of twice for NT = 39/40.
+//   ACRO_TS_PANN    12   nodes per panel (16: same answers to 5e-10, +14 % time; 10: 1.9e-8 and -15 %; 8: 1e-6, rejected)
+//   ACRO_TS_HC      2.0  width of the coarse panels [e-folds]
+//   ACRO_TS_MAXPAN  28   panels per point (12 fine + 12 coarse for a 2-decade T range; 17 + 11 for 4 decades)
+//   ACRO_TS_TOPX    50   top of the grid in units of Tmax (200 = the reference's cut-off: same results, +9 % time)
+//   ACRO_TS_FISSION 2    node values evaluated together in the panel loop (1: +7 % time; 3 and more: the loop body outgrows
+//                        the 6 KB L0 instruction cache and loses again)
+//   ACRO_TS_TILES   4    tiles of 256 pairs per block and Bose-table fill (1: +20 %; 8 and more: tail of unequal blocks)
+//   ACRO_TS_THREADS 256  threads per block (320 at 168 registers: spills, +13 %)
 #pragma once
 #include "acro_fastquad.cuh"
 
 namespace acro {
 
-constexpr int kTileScalars = 8;   // per-temperature scalars of a tile kept in shared memory (kernels_shared_kernel)
-#ifndef ACRO_TS_UNROLL
-#define ACRO_TS_UNROLL 1
+#ifndef ACRO_TS_TT
+#define ACRO_TS_TT 40
 #endif
-#ifndef ACRO_TS_TILES
-#define ACRO_TS_TILES 4      // tiles of kSharedThreads pairs per block (one Bose table fill serves all of them)
+#ifndef ACRO_TS_PANN
+#define ACRO_TS_PANN 12
+#endif
+#ifndef ACRO_TS_HC
+#define ACRO_TS_HC 2.0
+#endif
+#ifndef ACRO_TS_MAXPAN
+#define ACRO_TS_MAXPAN 28
 #endif
 #ifndef ACRO_TS_TOPX
 #define ACRO_TS_TOPX 50.0
 #endif
 #ifndef ACRO_TS_FISSION
-#define ACRO_TS_FISSION 2    // nodes evaluated together in the panel loop
+#define ACRO_TS_FISSION 2
 #endif
-#ifndef ACRO_TS_HC
-#define ACRO_TS_HC 2.0
+#ifndef ACRO_TS_TILES
+#define ACRO_TS_TILES 4
 #endif
-#ifndef ACRO_TS_TT
-#define ACRO_TS_TT 40
-#endif
-#ifndef ACRO_TS_MAXPAN
-#define ACRO_TS_MAXPAN 28
-#endif
-#ifndef ACRO_TS_CTAS
-#define ACRO_TS_CTAS 1
-#endif
-// Measured (168-point sample of the benchmark slice): 40 temperatures per tile with ONE 256-thread block per SM (255
-// registers, no spills to speak of) beats 20 per tile with two blocks (128 registers, spills) by 18 %: F/G are evaluated
-// once per node instead of twice for the default NT = 39/40, and the 40 independent FMAs per node hide the latency.
-constexpr int kTT = ACRO_TS_TT;         // temperatures per tile (accumulators per thread)
-constexpr double kHC = ACRO_TS_HC;   // width of the coarse panels [e-folds]
-#ifndef ACRO_TS_PANN
-#define ACRO_TS_PANN 12
-#endif
-constexpr int kPanN = ACRO_TS_PANN;       // Gauss-Legendre nodes per panel (12 or 16)
-constexpr int kMaxPan = ACRO_TS_MAXPAN;     // panels per point (12 fine + 12 coarse for a 2-decade T range; 17 + 11 for 4 decades)
 #ifndef ACRO_TS_THREADS
 #define ACRO_TS_THREADS 256
 #endif
-constexpr double kTopX = ACRO_TS_TOPX;       // top of the shared grid in units of the point's highest temperature
+constexpr int kTT = ACRO_TS_TT;
+constexpr int kPanN = ACRO_TS_PANN;
+constexpr double kHC = ACRO_TS_HC;
+constexpr int kMaxPan = ACRO_TS_MAXPAN;
+constexpr double kTopX = ACRO_TS_TOPX;
 constexpr int kSharedThreads = ACRO_TS_THREADS;
 constexpr int kTilesPerBlock = ACRO_TS_TILES;
+constexpr int kTileScalars = 8;   // per-temperature scalars of a tile kept in shared memory (kernels_shared_kernel)
 
 __constant__ double c_leg_modal[kPanN][kPanN];   // (2j+1)/2 * w_m * P_j(x_m): Legendre coefficients from nodal values
 __constant__ double c_leg_rec[kPanN][2];         // recurrence P_{j+1} = a_j t P_j - b_j P_{j-1}: a_j = (2j+1)/(j+1), b_j = j/(j+1)
@@ -288,7 +293,7 @@ __device__ __forceinline__ void shared_integral(const PairConst& c, double x_a, 
 // One thread owns one (E,E') pair of one model point and produces the five kernel planes for ALL temperatures of the
 // point: closed forms (pair-only parts computed once) and the temperature-shared integrals.  The (pair, T) combinations
 // whose lower limit sits on the Wien tail are completed by kernels_wien_kernel (below).
-__global__ void __launch_bounds__(kSharedThreads, ACRO_TS_CTAS) kernels_shared_kernel(acro_batch_t b, double* __restrict__ Kws, DeviceTables tb,
+__global__ void __launch_bounds__(kSharedThreads, 1) kernels_shared_kernel(acro_batch_t b, double* __restrict__ Kws, DeviceTables tb,
                                                                           acro_params_t p) {
     extern __shared__ double sm[];
     const int pt = blockIdx.y;
