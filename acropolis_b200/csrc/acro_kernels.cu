@@ -41,7 +41,13 @@ __host__ __device__ constexpr int gl_offset(int order) {
 
 }  // namespace acro
 #include "acro_fastquad.cuh"
+// 1: kernels_shared4_kernel (four lanes per pair, acro_tshared4.cuh), the production form; 0: kernels_shared_kernel (one
+// thread per pair, acro_tshared.cuh), kept as the build-time alternative it was derived from and is checked against
+#ifndef ACRO_TS_LANES4
+#define ACRO_TS_LANES4 1
+#endif
 #include "acro_tshared.cuh"
+#include "acro_tshared4.cuh"
 namespace acro {
 
 static void gauss_laguerre(int n, double* x, double* w) {   // alpha = 0; Newton on L_n with the classic initial guesses
@@ -1204,6 +1210,19 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
             const size_t smem_tables = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT +
                                                          (kTileScalars + 1) * kTT + (ACRO_FQ_LOGTAB ? 2 * kLogTab : 0));
             cudaError_t e = cudaSuccess;
+#if ACRO_TS_LANES4
+            const size_t smem = smem_tables + sizeof(double) * (kPanN * kPanN + (size_t)kL4Warps * kPanN * 8 +
+                                                                (size_t)kL4Warps * L4_NCONST * 32);
+            const int64_t passes_max = (tri_max + kL4Pairs - 1) / kL4Pairs;
+            grid.x = (unsigned)((passes_max + kL4PassesPerBlock - 1) / kL4PassesPerBlock);
+            static bool attr_set = false;
+            if (!attr_set) {
+                e = cudaFuncSetAttribute(kernels_shared4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set = (e == cudaSuccess);
+            }
+            if (e != cudaSuccess) return e;
+            kernels_shared4_kernel<<<grid, kL4Threads, smem, st>>>(b, Kws, t, p);
+#else
             const size_t smem = smem_tables + sizeof(double) * (size_t)kTT * kSharedThreads;
             static bool attr_set = false;
             if (!attr_set) {
@@ -1212,6 +1231,7 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
             }
             if (e != cudaSuccess) return e;
             kernels_shared_kernel<<<grid, kSharedThreads, smem, st>>>(b, Kws, t, p);
+#endif
             lc.launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (lc.split) lc.split_valid = cudaEventRecord(lc.split, st) == cudaSuccess;
