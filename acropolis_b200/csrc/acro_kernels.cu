@@ -1221,6 +1221,12 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
                 attr_set = (e == cudaSuccess);
             }
             if (e != cudaSuccess) return e;
+            {
+                dim3 gp((unsigned)((tri_max + 127) / 128), (unsigned)b.n_points);
+                pair_closed_forms_kernel<<<gp, 128, 0, st>>>(b, Kws);
+                lc.launches++;
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            }
             kernels_shared4_kernel<<<grid, kL4Threads, smem, st>>>(b, Kws, t, p);
 #else
             const size_t smem = smem_tables + sizeof(double) * (size_t)kTT * kSharedThreads;

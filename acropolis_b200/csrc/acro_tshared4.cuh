@@ -169,6 +169,31 @@ __device__ __forceinline__ void shared_integral4(int kind, const PairConst& c, d
     }
 }
 
+// Pair-only closed forms (Compton shapes per unit electron density, Bethe-Heitler dsigma/dE for Z^2 = 1; cascade.py:383-402,
+// 621-639) of every (E,E') pair of every point, thread per (point, pair).  They are ~1000 instructions that
+// kernels_shared4_kernel would otherwise execute once per 32 pairs in the middle of its hot loops (instruction cache!); here
+// they are parked in the point's OWN kernel-plane slots of its LAST temperature (planes 0, 1, 2): the main kernel reads them
+// at the start of a pass and overwrites them with the final values only in the epilogue of the last temperature tile.
+__global__ void __launch_bounds__(128) pair_closed_forms_kernel(acro_batch_t b, double* __restrict__ Kws) {
+    const int pt = blockIdx.y;
+    const int ne = b.pt_ne[pt];
+    const int64_t tri = (int64_t)ne * (ne + 1) / 2;
+    const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc >= tri) return;
+    const double tn = 2.0 * ne + 1.0;
+    int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+    i = max(0, min(i, ne - 1));
+    while (i > 0 && tri_row_off(i, ne) > loc) --i;
+    while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
+    const int j = i + (int)(loc - tri_row_off(i, ne));
+    const double* eg = b.e_grid + b.pt_e_off[pt];
+    const double E = eg[i], Ep = eg[j];
+    const int64_t o = b.sys_k_off[b.pt_sys_off[pt] + b.pt_nt[pt] - 1] + loc, np = b.n_pairs_total;
+    Kws[o] = kernel_compton_core(E, Ep, 1.0);
+    Kws[np + o] = kernel_compton_core(Ep + kMe - E, Ep, 1.0);
+    Kws[2 * np + o] = !(Ep < E + kMe) ? bh_dsdE_Z2(E, Ep) : 0.0;        // the condition of pair_limits(): xa9 > 0
+}
+
 __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_batch_t b, double* __restrict__ Kws, DeviceTables tb,
                                                                         acro_params_t p) {
     extern __shared__ double sm[];
@@ -208,6 +233,7 @@ __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_bat
     const double x_bot = exp(g.y_bot);
     const bool deep = x_bot <= 2e-11 * Tmin;
     const int64_t np = b.n_pairs_total;
+    const int64_t k_park = b.sys_k_off[s0 + nt - 1];     // where pair_closed_forms_kernel parked the closed forms
     const int tq = q * kL4T;                            // first temperature of this lane
     const double a2 = kAlpha * kAlpha;
 
@@ -267,9 +293,12 @@ __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_bat
                 cw[L4_XA9 * 32 + lane] = L.xa9; cw[L4_XB9 * 32 + lane] = L.xb9;
                 cw[L4_XA10 * 32 + lane] = L.xa10; cw[L4_XB10 * 32 + lane] = L.xb10;
                 cw[L4_XA11 * 32 + lane] = L.xa11; cw[L4_XB11 * 32 + lane] = L.xb11;
-                cw[L4_CG * 32 + lane] = kernel_compton_core(E, Ep, 1.0);
-                cw[L4_CE * 32 + lane] = kernel_compton_core(Ep + kMe - E, Ep, 1.0);
-                cw[L4_BH * 32 + lane] = (L.xa9 > 0.0) ? bh_dsdE_Z2(E, Ep) : 0.0;
+                {
+                    const int64_t o = k_park + (active ? loc : 0);
+                    cw[L4_CG * 32 + lane] = Kws[o];
+                    cw[L4_CE * 32 + lane] = Kws[np + o];
+                    cw[L4_BH * 32 + lane] = Kws[2 * np + o];
+                }
                 cw[L4_PP * 32 + lane] = 1112.0 / (10125.0 * kPi) * (a2 * a2) / ((kMe2 * kMe2) * (kMe2 * kMe2)) * 8.0 * (kPi2 * kPi2) /
                                         63.0 * (Ep * Ep) * (gg_shape * gg_shape);
                 cw[L4_C9 * 32 + lane] = r * r / (2.0 + 2.0 * r);
