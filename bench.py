@@ -294,11 +294,11 @@ def main_gpu(args):
     hbm_peak = hbm_peak or 6650.0
     solve_bytes = 5 * 8 * pairs       # the solve stage reads every K entry once (G, F, S0 are <1% of that)
     # DRAM traffic and executed-FP64 utilisation of the two kernel-builder kernels from the committed ncu captures of one
-    # slice (profiles/r01_ncu_kernels_shared_kernel.txt, r01_ncu_kernels_wien_kernel.txt): bytes per slice, i.e. per launch pair
-    ncu = {"traffic_bytes_per_launch": 21.43e9 + 9.43e9, "algorithmic_bytes_per_launch": 5 * 8 * pairs / max(k_launches, 1),
-           "fp64_pipe_active_pct": {"kernels_shared_kernel": 39.9, "kernels_wien_kernel": 54.2},
-           "issue_active_pct": {"kernels_shared_kernel": 40.0, "kernels_wien_kernel": 66.2},
-           "source": "profiles/r01_ncu_kernels_shared_kernel.txt, profiles/r01_ncu_kernels_wien_kernel.txt"}
+    # slice (profiles/r01_ncu_kernels_shared4_kernel.txt, r01_ncu_kernels_wien_kernel.txt): bytes per slice, i.e. per launch pair
+    ncu = {"traffic_bytes_per_launch": 36.56e9 + 9.58e9, "algorithmic_bytes_per_launch": 5 * 8 * pairs / max(k_launches, 1),
+           "fp64_pipe_active_pct": {"kernels_shared4_kernel": 36.5, "kernels_wien_kernel": 54.9},
+           "issue_active_pct": {"kernels_shared4_kernel": 45.3, "kernels_wien_kernel": 65.8},
+           "source": "profiles/r01_ncu_kernels_shared4_kernel.txt, profiles/r01_ncu_kernels_wien_kernel.txt"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config({"chunks_per_step": len(staged[-1])}),
@@ -306,7 +306,7 @@ def main_gpu(args):
                     "api": "acropolis_b200.scans.run_points (model construction + source arrays + pinned H2D + kernels + D2H)",
                     "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": int(dev_launches), "gpu_launches_total_all_arms": int(total_launches),
-            "roofline": {"kernel": "kernel builder, stage (i): kernels_shared_kernel + kernels_wien_kernel<%d>" % prm.quad_order,
+            "roofline": {"kernel": "kernel builder, stage (i): pair_closed_forms_kernel + kernels_shared4_kernel + kernels_wien_kernel<%d>" % prm.quad_order,
                          "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": ncu["traffic_bytes_per_launch"],
                          "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
