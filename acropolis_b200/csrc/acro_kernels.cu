@@ -1211,7 +1211,7 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
                                                          (kTileScalars + 1) * kTT + (ACRO_FQ_LOGTAB ? 2 * kLogTab : 0));
             cudaError_t e = cudaSuccess;
 #if ACRO_TS_LANES4
-            const size_t smem = smem_tables + sizeof(double) * (kPanN * kPanN + (size_t)kL4Warps * kPanN * 8 +
+            const size_t smem = smem_tables + sizeof(double) * (kPanN * kPanN + (size_t)kL4Warps * kPanN * kL4PW +
                                                                 (size_t)kL4Warps * L4_NCONST * 32);
             const int64_t passes_max = (tri_max + kL4Pairs - 1) / kL4Pairs;
             grid.x = (unsigned)((passes_max + kL4PassesPerBlock - 1) / kL4PassesPerBlock);

@@ -24,9 +24,18 @@ namespace acro {
 constexpr int kL4Threads = 512;
 constexpr int kL4Warps = kL4Threads / 32;
 constexpr int kL4Pairs = kL4Warps * 32;     // pairs per macro-pass of a block (32 per warp)
-constexpr int kL4T = kTT / 4;               // temperatures per lane
-constexpr int kL4N = kPanN / 4;             // nodes per lane
-static_assert(kTT % 8 == 0 && kPanN % 4 == 0, "tile and panel must split over four lanes (LDS.128 needs an even share)");
+#ifndef ACRO_L4_LANES
+#define ACRO_L4_LANES 4                     // lanes that share one pair: 4 or 2
+#endif
+constexpr int kLP = ACRO_L4_LANES;
+constexpr int kLPshift = kLP == 4 ? 2 : 1;
+constexpr int kL4PW = 32 / kLP;             // pairs per sub-pass of a warp
+constexpr int kL4T = kTT / kLP;             // temperatures per lane
+constexpr int kL4N = kPanN / kLP;           // nodes per lane
+constexpr int kL4G = 3;                     // node values evaluated together (independent chains)
+static_assert(kLP == 2 || kLP == 4, "two or four lanes per pair");
+static_assert(kTT % (2 * kLP) == 0 && kPanN % kLP == 0 && kL4N % kL4G == 0,
+              "tile and panel must split over the lanes (LDS.128 needs an even share)");
 #ifndef ACRO_L4_PASSES
 #define ACRO_L4_PASSES 2                    // macro-passes (512 pairs each) per block and Bose-table fill
 #endif
@@ -53,7 +62,7 @@ __device__ __forceinline__ void add_moments4(int kind, const PairConst& c, doubl
     const double ic = 2.0 / h, mid = p_lo + 0.5 * h;
 #pragma unroll 1
     for (int ss = 0; ss < kL4N; ++ss) {
-        const int s = q + 4 * ss;
+        const int s = q + kLP * ss;
         const double y = fma(hp, c_glx[gl_offset(kPanN) + s], mp);
         const double x = fexp(y);
         double f = node_core(kind, c, x, frcp(x), y, x_a, lna);
@@ -72,7 +81,7 @@ __device__ __forceinline__ void add_moments4(int kind, const PairConst& c, doubl
 }
 
 // Partial panel of one pair, executed by its four lanes together (all lanes of the warp call it; `on` marks the pairs that
-// really have a partial panel here, the others publish zeros).  Publishes the 12 node weights of the pair in wp[node * 8].
+// really have a partial panel here, the others publish zeros).  Publishes the 12 node weights of the pair in wp[node * kL4PW].
 __device__ __forceinline__ void partial_panel4(int kind, const PairConst& c, double x_a, double lna, double lo_y, double hi_y,
                                                double p_lo, double h, double y_layer, int q, bool on,
                                                const double* __restrict__ s_modal, double* __restrict__ wp) {
@@ -90,7 +99,7 @@ __device__ __forceinline__ void partial_panel4(int kind, const PairConst& c, dou
 #pragma unroll
     for (int j = 0; j < kPanN; ++j) {
         mu[j] += __shfl_xor_sync(0xffffffffu, mu[j], 1);
-        mu[j] += __shfl_xor_sync(0xffffffffu, mu[j], 2);
+        if (kLP == 4) mu[j] += __shfl_xor_sync(0xffffffffu, mu[j], 2);
     }
 #pragma unroll
     for (int mm = 0; mm < kL4N; ++mm) {
@@ -98,7 +107,7 @@ __device__ __forceinline__ void partial_panel4(int kind, const PairConst& c, dou
         double v = 0.0;
 #pragma unroll
         for (int j = 0; j < kPanN; ++j) v = fma(s_modal[j * kPanN + m], mu[j], v);
-        wp[m * 8] = on ? v : 0.0;
+        wp[m * kL4PW] = on ? v : 0.0;
     }
 }
 
@@ -147,21 +156,24 @@ __device__ __forceinline__ void shared_integral4(int kind, const PairConst& c, d
         }
         if (any_full) {
             const double wscale = full ? 0.5 * h : 0.0;
-            double fv[kL4N];
+#pragma unroll 1
+            for (int m0 = kL4N * q; m0 < kL4N * (q + 1); m0 += kL4G) {
+                double fv[kL4G];
 #pragma unroll
-            for (int mm = 0; mm < kL4N; ++mm) {
-                const int m = kL4N * q + mm;
-                const int k = base + m;
-                fv[mm] = node_core(kind, c, sx[k], six[k], sy[k], x_a, lna) * (c_glw[gl_offset(kPanN) + m] * wscale);
+                for (int mm = 0; mm < kL4G; ++mm) {
+                    const int m = m0 + mm;
+                    const int k = base + m;
+                    fv[mm] = node_core(kind, c, sx[k], six[k], sy[k], x_a, lna) * (c_glw[gl_offset(kPanN) + m] * wscale);
+                }
+#pragma unroll
+                for (int mm = 0; mm < kL4G; ++mm)
+                    if (full || !any_part) wp[(m0 + mm) * kL4PW] = full ? fv[mm] : 0.0;   // partial pairs keep their weights
             }
-#pragma unroll
-            for (int mm = 0; mm < kL4N; ++mm)
-                if (full || !any_part) wp[(kL4N * q + mm) * 8] = full ? fv[mm] : 0.0;   // partial pairs keep their weights
         }
         __syncwarp();                           // weights of all pairs are published
 #pragma unroll 4
         for (int m = 0; m < kPanN; ++m) {
-            const double v = wp[m * 8];
+            const double v = wp[m * kL4PW];
             const double* __restrict__ Bk = sBq + (size_t)(base + m) * kTT;
 #pragma unroll
             for (int t = 0; t < kL4T; ++t) acc[t] = fma(v, Bk[t], acc[t]);
@@ -216,7 +228,7 @@ __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_bat
     double2* s_lt = reinterpret_cast<double2*>(sT + (kTileScalars + 1) * kTT);
     double* s_modal = reinterpret_cast<double*>(s_lt + kLogTab);          // [kPanN][kPanN] copy of c_leg_modal
     double* s_w = s_modal + kPanN * kPanN;                                 // [warps][kPanN][8]
-    double* s_c = s_w + (size_t)kL4Warps * kPanN * 8;                      // [warps][L4_NCONST][32]
+    double* s_c = s_w + (size_t)kL4Warps * kPanN * kL4PW;                      // [warps][L4_NCONST][32]
     for (int k = threadIdx.x; k < kLogTab; k += blockDim.x) s_lt[k] = g_logtab[k];
     for (int k = threadIdx.x; k < kPanN * kPanN; k += blockDim.x) s_modal[k] = c_leg_modal[k / kPanN][k % kPanN];
     for (int k = threadIdx.x; k < nn; k += blockDim.x) {
@@ -227,8 +239,8 @@ __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_bat
         sy[k] = y; sx[k] = x; six[k] = frcp(x);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = lane & 3, pw = lane >> 2;             // quarter of the pair's work, pair within the sub-pass
-    double* w = s_w + (size_t)warp * kPanN * 8;
+    const int q = lane & (kLP - 1), pw = lane >> kLPshift;             // quarter of the pair's work, pair within the sub-pass
+    double* w = s_w + (size_t)warp * kPanN * kL4PW;
     double* cw = s_c + (size_t)warp * L4_NCONST * 32;
     const double x_bot = exp(g.y_bot);
     const bool deep = x_bot <= 2e-11 * Tmin;
@@ -309,8 +321,8 @@ __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_bat
             __syncwarp();
             // ---- phase B: four lanes per pair, 8 pairs at a time
 #pragma unroll 1
-            for (int sub = 0; sub < 4; ++sub) {
-                const int pp = sub * 8 + pw;
+            for (int sub = 0; sub < kLP; ++sub) {
+                const int pp = sub * kL4PW + pw;
                 const int64_t loc = loc0 + pp;
                 const bool active = cw[L4_ACTIVE * 32 + pp] != 0.0;
                 const double E = cw[L4_E * 32 + pp], Ep = cw[L4_EP * 32 + pp];
