@@ -284,6 +284,15 @@ class Engine(object):
     def stage(self, pts, want=("Yf", "status"), resident=False):
         """Assemble a chunk on the host, copy it to the device (one pinned H2D) and allocate its outputs.  With
         ``resident`` the chunk gets its own device buffers (it can be launched repeatedly, e.g. by the benchmark)."""
+        # heaviest points first: blocks are scheduled in index order, and a launch that ends with the longest blocks of the
+        # largest points has the longest tail (measured: 1.1 ms of an 80 ms slice).  `perm[k]` = input index of sorted point k;
+        # _collect() puts the outputs back into input order.
+        cost = np.fromiter((len(p.T) * len(p.E_grid) ** 2 for p in pts), dtype=np.int64, count=len(pts))
+        perm = np.argsort(-cost, kind="stable")
+        if np.array_equal(perm, np.arange(len(pts))):
+            perm = None
+        else:
+            pts = [pts[i] for i in perm]
         a, cnt = self.assemble(pts)
         st = self.stream
         arena = _Arena(self.device) if resident else self._arena_for_chunk()
@@ -318,7 +327,7 @@ class Engine(object):
         o = _lib.Out()
         for k, t in outs.items():
             setattr(o, k, t.data_ptr())
-        return dict(cnt=cnt, batch=b, out=o, outs=outs, keep=(a, arena))
+        return dict(cnt=cnt, batch=b, out=o, outs=outs, keep=(a, arena), perm=perm, ne=a["pt_ne"], nt=a["pt_nt"])
 
     def launch(self, ch, stages=_lib.STAGE_ALL):
         """Enqueue the stages of a staged chunk on the engine's stream (asynchronous)."""
@@ -336,7 +345,7 @@ class Engine(object):
                 self.last_d2h_bytes = getattr(self, "last_d2h_bytes", 0) + host[k].numel() * host[k].element_size()
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return dict(host=host, ev=ev, cnt=ch["cnt"], keep=ch, batch=ch["batch"])
+        return dict(host=host, ev=ev, cnt=ch["cnt"], keep=ch, batch=ch["batch"], perm=ch["perm"], ne=ch["ne"], nt=ch["nt"])
 
     def count_work(self, ch):
         """(pairs, N_a9, N_a10, N_a11) of a staged chunk (SURVEY.md 8d work census)."""
@@ -368,7 +377,21 @@ class Engine(object):
         shapes = dict(Yf=(cnt["n_points"], 9, 3), mpdi=(cnt["n_points"], 9, 9), mdcy=(cnt["n_points"], 9, 9),
                       status=(cnt["n_points"],), pdi=(cnt["n_systems"], _lib.NR), G=(-1,), F=(-1,))
         for k, t in pnd["host"].items():
-            res[k].append(t.numpy().reshape(shapes[k]).copy())
+            res[k].append(self.unpermute(k, t.numpy().reshape(shapes[k]), pnd["perm"], pnd["ne"], pnd["nt"]))
+
+    @staticmethod
+    def unpermute(key, arr, perm, ne, nt):
+        """Output `key` of a chunk that stage() sorted by cost, back in the caller's point order (a copy in any case)."""
+        if perm is None:
+            return arr.copy()
+        if key in ("Yf", "mpdi", "mdcy", "status"):          # one row per point
+            out = np.empty_like(arr)
+            out[perm] = arr
+            return out
+        seg = (nt if key == "pdi" else 3 * ne.astype(np.int64) * nt).astype(np.int64)     # rows / values per sorted point
+        start = np.concatenate(([0], np.cumsum(seg)))
+        inv = np.argsort(perm)                                # sorted position of input point i
+        return np.concatenate([arr[start[k]:start[k + 1]] for k in inv]) if len(inv) else arr.copy()
 
     # ------------------------------------------------------------------------------------------------------
     def kernels_of(self, point, it):

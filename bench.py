@@ -257,7 +257,8 @@ def main_gpu(args):
             stage_ms += eng.stage_ms()
             k_launches += 1
     value = world * K * per_step / (ms_dev * 1e-3)
-    yf_check = staged[-1][0]["outs"]["Yf"].cpu().numpy()
+    ch0 = staged[-1][0]
+    yf_check = eng.unpermute("Yf", ch0["outs"]["Yf"].cpu().numpy().reshape(-1, 9, 3), ch0["perm"], ch0["ne"], ch0["nt"])
     assert np.all(np.isfinite(yf_check)), "non-finite abundances in the benchmark batch"
 
     # ---- end-to-end arm: public API, host buffers in, host rows out ------------------------------------------------

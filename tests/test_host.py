@@ -251,3 +251,23 @@ def test_resonance_model_hooks_match_reference():
     from acropolis_b200.ext.models import ResonanceModel
     with pytest.raises(AcropolisError):
         ResonanceModel(10., 2.0, 1e-3, 1e-12, 1, 1e-3)     # delta > 1
+
+
+def test_unpermute_outputs_of_a_cost_sorted_chunk():
+    """Engine.stage sorts a chunk heaviest-first; Engine.unpermute must put per-point, per-system and per-(system,E)
+    outputs back into the caller's order."""
+    from acropolis_b200.engine import Engine
+    rng = np.random.default_rng(3)
+    ne_in = np.array([5, 9, 3, 7]); nt_in = np.array([2, 1, 4, 3])          # caller's order
+    perm = np.argsort(-(nt_in * ne_in ** 2), kind="stable")                  # as in Engine.stage
+    ne, nt = ne_in[perm], nt_in[perm]                                        # sorted order (what the device saw)
+    per_point = [rng.normal(size=(9, 3)) for _ in range(4)]
+    per_sys = [rng.normal(size=(t, 17)) for t in nt_in]
+    per_f = [rng.normal(size=3 * e * t) for e, t in zip(ne_in, nt_in)]
+    Yf = np.stack([per_point[i] for i in perm])
+    pdi = np.concatenate([per_sys[i] for i in perm])
+    F = np.concatenate([per_f[i] for i in perm])
+    assert np.array_equal(Engine.unpermute("Yf", Yf, perm, ne, nt), np.stack(per_point))
+    assert np.array_equal(Engine.unpermute("pdi", pdi, perm, ne, nt), np.concatenate(per_sys))
+    assert np.array_equal(Engine.unpermute("F", F, perm, ne, nt), np.concatenate(per_f))
+    assert np.array_equal(Engine.unpermute("Yf", Yf, None, ne, nt), Yf)
