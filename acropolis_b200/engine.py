@@ -30,6 +30,15 @@ class PointSpec(object):
         self.sc = sc        # SEPARABLE: [NT,3]; DENSE: [NT,3,NE]
         self.sc_E = sc_E    # SEPARABLE: [NE,3]
 
+    @classmethod
+    def trusted(cls, E0, E_grid, T, S0, t_at_tmax, sc_mode=_lib.SC_NONE, sc=None, sc_E=None):
+        """Constructor without conversions for callers that already hold contiguous float64 arrays of the right shapes
+        (the vectorised ``point_specs`` of the models: one call per scan point)."""
+        self = object.__new__(cls)
+        self.E0, self.E_grid, self.T, self.S0, self.t_at_tmax = E0, E_grid, T, S0, t_at_tmax
+        self.sc_mode, self.sc, self.sc_E = sc_mode, sc, sc_E
+        return self
+
 
 _GRID_MEMO = {}     # the points of a grid scan share their energy and temperature grids (read-only arrays)
 

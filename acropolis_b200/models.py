@@ -275,10 +275,10 @@ class DecayModel(AbstractModel):
             off += nt[k]
             E_grid = energy_grid(m._sE0)
             if m._sBRee == 0.:
-                specs.append(PointSpec(m._sE0, E_grid, Ts[k], S0_all[sl], t_tmax[k]))
+                specs.append(PointSpec.trusted(float(m._sE0), E_grid, Ts[k], S0_all[sl], float(t_tmax[k])))
             else:
-                specs.append(PointSpec(m._sE0, E_grid, Ts[k], S0_all[sl], t_tmax[k], _lib.SC_SEPARABLE, sc_all[sl],
-                                       _fsr_columns(E_grid, m._sE0)))
+                specs.append(PointSpec.trusted(float(m._sE0), E_grid, Ts[k], S0_all[sl], float(t_tmax[k]), _lib.SC_SEPARABLE,
+                                               sc_all[sl], _fsr_columns(E_grid, m._sE0)))
         return specs
 
 
