@@ -265,12 +265,13 @@ __device__ double direct_ic_lane(double E, double T, double Ephb_T_max, int lane
         double inner = 0.0;
         for (int j = 0; j < 96; ++j) {
             const double s  = ms + hs * xi[j];
-            const double w  = exp(s);
-            const double y  = E * expm1(s) / w;
-            const double q  = y / (Gm * (E - y));
+            const double em = expm1(s);                  // w - 1 to full relative accuracy (s can be ~1e-10)
+            const double iw = frcp(1.0 + em);            // 1/w
+            const double y  = E * em * iw;
+            const double q  = y * frcp(Gm * (E - y));
             const double Gq = Gm * q;
-            const double F  = 2.0 * q * log(q) + (1.0 + 2.0 * q) * (1.0 - q) + Gq * Gq * (1.0 - q) / (2.0 + 2.0 * Gq);
-            inner += wi[j] * F * E / w;
+            const double F  = 2.0 * q * flog(q) + (1.0 + 2.0 * q) * (1.0 - q) + Gq * Gq * (1.0 - q) * frcp(2.0 + 2.0 * Gq);
+            inner += wi[j] * F * E * iw;
         }
         inner *= hs;
         tot += h * wo[k] * inner * x / (kPi2 * expm1(x / T)) * x;
@@ -291,10 +292,10 @@ __device__ double direct_pc_lane(double E, double T, double Ephb_T_max, int lane
         for (int j = 0; j < 32; ++j) {
             const double v  = 0.5 * vmax * (1.0 + xi[j]);
             const double u  = v * v;
-            const double s  = 4.0 * kMe2 * exp(u);
-            const double b2 = -expm1(-u), bb = sqrt(b2);
+            const double b2 = -expm1(-u), bb = sqrt(b2);             // beta^2 = 1 - e^{-u} = 1 - 4 me^2/s
+            const double s  = 4.0 * kMe2 * frcp(1.0 - b2);           // e^{u} = 1/(1 - beta^2)
             const double sig = 0.5 * kPi * (kRe * kRe) * (1.0 - b2) *
-                               ((3.0 - b2 * b2) * log((1.0 + bb) / (1.0 - bb)) - 2.0 * bb * (2.0 - b2));
+                               ((3.0 - b2 * b2) * flog((1.0 + bb) * frcp(1.0 - bb)) - 2.0 * bb * (2.0 - b2));
             inner += wi[j] * s * sig * s * 2.0 * v;
         }
         inner *= 0.5 * vmax;
