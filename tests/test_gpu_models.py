@@ -237,3 +237,35 @@ def test_edge_cases(gpu_engine):
     assert np.all(np.isfinite(out["Yf"]))
     r = run_points(DecayModel, [dict(mphi=20., tau=1e6, temp0=10., n0a=1e-9, bree=0., braa=1.)], group=1)
     assert r.shape == (1, 6 + 27)
+
+
+def test_full_size_slice_invariants(gpu_engine):
+    """One 1000-point slice of BASELINE config 3 (the 200x200 mphi x tau scan, as bench.py cuts it) through the public
+    scan entry, checked with size-independent properties: (1) nucleon number sum_i A_i Y_i is conserved by the whole chain
+    (pre-decay, expm of the photodisintegration + decay matrix, post-decay) up to the accuracy of the matrix exponential,
+    u * ||mdcy||_1 = 1.6e-7 for the slice's largest decay matrix (||mdcy||_1 = 1.45e9 at tau = 7.5e8 s); measured 7.7e-8
+    (SciPy's structure-aware expm on the same matrices: 3e-9, tools/gpu_conservation_check.py); (2) points
+    below all thresholds return the decayed BBN abundances; (3) a point's row does not depend on what else is in the
+    batch (grouping, cost sorting and un-permutation of run_points / Engine.stage)."""
+    from acropolis_b200.models import DecayModel
+    from acropolis_b200.scans import run_points
+    fixed = dict(temp0=10., n0a=1e-10, bree=0., braa=1.)
+    grid = [dict(mphi=float(m), tau=float(t)) for m in np.logspace(0, 3, 200) for t in np.logspace(3, 10, 200)]
+    par = grid[7::40]
+    assert len(par) == 1000
+    rows = run_points(partial(DecayModel, **fixed), par)
+    assert rows.shape == (1000, 29) and np.all(np.isfinite(rows))
+    assert np.array_equal(rows[:, 0], [p["mphi"] for p in par]) and np.array_equal(rows[:, 1], [p["tau"] for p in par])
+    Y = rows[:, 2:].reshape(1000, 3, 9)                        # [point, (mean, high, low), nuclide]
+    A = np.array([1., 1., 2., 3., 3., 4., 6., 7., 7.])
+    m0 = DecayModel(1.0, 1e5, **fixed)
+    Y0 = m0._sII.bbn_abundances()                              # [nuclide, 3]
+    assert np.max(np.abs((Y @ A) / (A @ Y0)[None, :] - 1.)) < 5e-7
+    trivial = np.array([p["mphi"] / 2. <= 1.5 for p in par])
+    assert 100 < trivial.sum() < 300
+    Yt = m0._squeeze_decays(Y0)
+    assert np.array_equal(Y[trivial], np.broadcast_to(Yt.T, (int(trivial.sum()), 3, 9)))
+    rng = np.random.default_rng(11)
+    for k in rng.choice(np.flatnonzero(~trivial), 12, replace=False):
+        Yk = DecayModel(par[k]["mphi"], par[k]["tau"], **fixed).run_disintegration()
+        assert relerr(Y[k].T, Yk, 1e-30) < 1e-12, par[k]
