@@ -10,6 +10,7 @@ rows are gathered at the end -- no collective on the hot path.  Two ways to use 
 * one process per GPU under ``torchrun``: every rank calls ``perform_scan()``; ranks compute their shard and the
   rows are all-gathered so every rank returns the full table (``ACROPOLIS_B200_DIST=0`` disables this)."""
 from functools import partial
+import gc
 import os
 from time import time
 
@@ -146,16 +147,18 @@ def run_models(models, devices=None, want_matp=False):
     return (Yf, matp) if want_matp else Yf
 
 
-def run_points(model, param_sets, devices=None, group=2048, first_group=384, growth=8):
+def run_points(model, param_sets, devices=None, group=4096, first_group=64, growth=64):
     """Rows ``[sorted params..., 9 mean, 9 high, 9 low]`` for an arbitrary list of parameter dicts of one model class
     (or ``functools.partial``): the batched form of ``BufferedScanner._run_single`` (reference scans.py:110-124).
     Builds the models, stages their grids and source arrays, runs the CUDA path and reads the abundances back.  On one
     device the list is processed in groups: while the GPU works on one group the host constructs the models and source
-    arrays of the next.  The groups grow geometrically (`first_group`, then x`growth` up to `group`).  Measured on a
-    1000-point slice of the benchmark scan (tools/gpu_e2e_timeline.py; host ~12 us per point, GPU ~95 us): every extra
-    launch costs ~1 ms of GPU time (tails of the longest blocks) and the GPU idles while the host prepares a group that is
-    more than ~8x the previous one, so two groups (384 + rest: 92 ms wall for 84 ms of GPU work) beat both one group
-    (96 ms: nothing overlaps) and 32/128/512/rest (95 ms)."""
+    arrays of the next.  The first group is the LAST `first_group` GPU points of the list, launched before anything else
+    is constructed (scans are ordered by increasing mass, so the tail is the expensive end: 64 points of the benchmark
+    scan's tail are ~17 ms of GPU work, more than the host needs for the other 936); the rest is sorted heaviest-first by
+    the cost proxy NT * NE^2 and goes in groups that grow by `growth` up to `group`.  Any order is valid -- a list whose
+    tail is cheap only pipelines less well.  Measured on 1000-point slices (tools/gpu_e2e_timeline.py; host ~12 us per
+    point, GPU ~95 us on average but ~28 us for the light points a scan starts with): every extra launch costs ~1 ms of
+    GPU time, so two groups are the sweet spot; in scan order the best split (384 + rest) left 6 ms of pipeline fill."""
     import torch
     if devices is None:
         dist = _dist_world()
@@ -167,6 +170,20 @@ def run_points(model, param_sets, devices=None, group=2048, first_group=384, gro
         Yf = run_models(models, devices=devices)
         return np.array([[*[p[k] for k in sorted(p)], *Y.transpose().reshape(Y.size)] for p, Y in zip(param_sets, Yf)])
     rows, eng, in_flight = [None] * N, None, []
+    # The loop below allocates thousands of small objects per call; a generation-2 collection in the middle of it walks
+    # every cached grid and model (tens of ms, seen as 30-50 ms holes in tools/gpu_e2e_timeline.py) while the GPU runs dry.
+    # Nothing here creates reference cycles, so the collector rests until the rows are assembled.
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        return _run_points_pipelined(model, param_sets, devices, group, first_group, growth, rows, eng, in_flight)
+    finally:
+        if gc_was_on:
+            gc.enable()
+
+
+def _run_points_pipelined(model, param_sets, devices, group, first_group, growth, rows, eng, in_flight):
+    N = len(param_sets)
 
     def finish(entry):
         idx, pend = entry
@@ -176,37 +193,52 @@ def run_points(model, param_sets, devices=None, group=2048, first_group=384, gro
             p = param_sets[i]
             rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
 
-    ncol = 3
-    # groups are counted in points that NEED the GPU (points below all thresholds are answered on the spot and a scan
-    # may start with hundreds of them); a small first group gets the GPU going early, then `group` points at a time
-    idx, todo, first, target = [], [], True, min(group, first_group)
+    models, ncol = [None] * N, 3
 
-    def flush():
-        nonlocal idx, todo, first
-        if todo:
-            specs = type(todo[0]).point_specs(todo) if len({type(m) for m in todo}) == 1 else [m.point_spec() for m in todo]
-            in_flight.append((idx, eng.submit(specs, want=("Yf", "status"))))
-            idx, todo, first = [], [], False
+    def build(i):
+        """Model of point i; a point below all thresholds is answered on the spot (a scan may start with hundreds)."""
+        nonlocal ncol, eng
+        m = models[i] = model(**param_sets[i])
+        if m.is_trivial():
+            Y = m._squeeze_decays(m._sII.bbn_abundances())
+            ncol = Y.shape[1]
+            p = param_sets[i]
+            rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
+            return False
+        if eng is None:
+            ncol = m._sII.bbn_abundances().shape[1]
+            eng = Engine.get(m._sII, devices[0])
+            eng.last_h2d_bytes = eng.last_d2h_bytes = 0
+        return True
+
+    def submit(idx):
+        todo = [models[i] for i in idx]
+        specs = type(todo[0]).point_specs(todo) if len({type(mm) for mm in todo}) == 1 else [mm.point_spec() for mm in todo]
+        in_flight.append((idx, eng.submit(specs, want=("Yf", "status"))))
         while len(in_flight) > 2:
             finish(in_flight.pop(0))
 
-    for i in range(N):
-        m = model(**param_sets[i])
-        ncol = m._sII.bbn_abundances().shape[1]
-        if m.is_trivial():
-            Y = m._squeeze_decays(m._sII.bbn_abundances())
-            p = param_sets[i]
-            rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
-            continue
-        if eng is None:
-            eng = Engine.get(m._sII, devices[0])
-            eng.last_h2d_bytes = eng.last_d2h_bytes = 0
-        idx.append(i)
-        todo.append(m)
-        if len(todo) >= target:
-            flush()
-            target = min(group, growth * target)     # see the docstring
-    flush()
+    # 1. first group: the last `first_group` GPU points of the list, before anything else is even constructed
+    head, i = [], N - 1
+    while i >= 0 and len(head) < min(group, first_group):
+        if build(i):
+            head.append(i)
+        i -= 1
+    if head:
+        submit(head)
+    # 2. the rest: all models, then heaviest first by the cost proxy NT * NE^2 of the grids they imply
+    gpu_idx = [k for k in range(i + 1) if build(k)]
+    if gpu_idx:
+        E0 = np.array([models[k]._sE0 for k in gpu_idx], dtype=np.float64)
+        Tr = np.array([models[k]._sTrg for k in gpu_idx], dtype=np.float64)
+        ne = np.maximum((np.log10(E0 / params.Emin) * params.NE_pd).astype(np.int64), params.NE_min)
+        nt = (np.log10(Tr[:, 1] / Tr[:, 0]) * params.NT_pd).astype(np.int64)
+        order = [gpu_idx[k] for k in np.argsort(-(nt * ne * ne), kind="stable")]
+        k, target = 0, min(group, growth * max(1, len(head)))
+        while k < len(order):
+            submit(order[k:k + target])
+            k += target
+            target = min(group, growth * target)
     for entry in in_flight:
         finish(entry)
     return np.array(rows)

@@ -18,8 +18,8 @@ def launch(self, ch, stages=7 | 8):
     evs.append((a, b, ch["cnt"]["n_points"], time.perf_counter()))
 Engine.launch = launch
 import itertools
-CFG = [(384, 8)]
-for (fg, gr), rep in itertools.product(CFG, range(4)):
+CFG = [(64, 64)]
+for (fg, gr), rep in itertools.product(CFG, range(8)):
     par = slice_params(pts, rep)
     torch.cuda.synchronize()
     del evs[:]
