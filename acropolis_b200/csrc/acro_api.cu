@@ -121,14 +121,15 @@ int acro_set_params(acro_handle_t* h, const acro_params_t* p) {
     return ACRO_OK;
 }
 
-// workspace layout: [5 K planes][direct-rate items][item counter (256 B)][per-system status]
+// workspace layout: [5 K planes][direct-rate items][cross-section table of the pdi cells][item counter (256 B)][per-system status]
 static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
-struct WsLayout { int64_t k, items, counter, status, total; };
+struct WsLayout { int64_t k, items, sig, counter, status, total; };
 static WsLayout ws_layout(const acro_batch_t* b) {
     WsLayout w;
     w.k = 0;
     w.items = align256((int64_t)ACRO_NK * b->n_pairs_total * (int64_t)sizeof(double));
-    w.counter = w.items + align256(b->n_sys_energy_total * (int64_t)sizeof(DirectRateItem));
+    w.sig = w.items + align256(b->n_sys_energy_total * (int64_t)sizeof(DirectRateItem));
+    w.counter = w.sig + align256((int64_t)16 * ACRO_NR * b->n_energy_total * (int64_t)sizeof(double));   // up to 16 nodes per cell
     w.status = w.counter + 256;
     w.total = w.status + align256((int64_t)b->n_systems * (int64_t)sizeof(int));
     return w;
@@ -170,7 +171,7 @@ int acro_run_batch(acro_handle_t* h, const acro_batch_t* b, const acro_out_t* o,
     CU(h, cudaEventRecord(h->ev[1], st));
     if (stages & ACRO_STAGE_KERNELS) CU(h, launch_kernels(*b, h->tables, h->params, Kws, st, h->lc));
     CU(h, cudaEventRecord(h->ev[2], st));
-    if (stages & ACRO_STAGE_SOLVE) CU(h, launch_solve_pdi(*b, *o, h->tables, h->params, Kws, st, h->lc));
+    if (stages & ACRO_STAGE_SOLVE) CU(h, launch_solve_pdi(*b, *o, h->tables, h->params, Kws, (double*)(base + w.sig), st, h->lc));
     CU(h, cudaEventRecord(h->ev[3], st));
     if (stages & ACRO_STAGE_MATRIX)
         CU(h, launch_matrix(b->n_points, b->pt_nt, b->pt_sys_off, b->sys_T, o->pdi, nullptr, b->pt_t_at_tmax,

@@ -45,7 +45,7 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
 cudaError_t launch_count_work(const acro_batch_t& b, const acro_params_t& p, unsigned long long* out, cudaStream_t st,
                               LaunchCounters& lc);
 cudaError_t launch_solve_pdi(const acro_batch_t& b, const acro_out_t& o, const DeviceTables& t, const acro_params_t& p,
-                             const double* Kws, cudaStream_t st, LaunchCounters& lc);
+                             const double* Kws, double* sig, cudaStream_t st, LaunchCounters& lc);
 cudaError_t launch_matrix(int n_points, const int32_t* pt_nt, const int32_t* pt_sys_off, const double* sys_T,
                           const double* pdi, const double* T_lo, const double* pt_t_at_tmax, const int* status_sys,
                           const double* pt_e0, int nt_max, double* mpdi, double* mdcy, double* Yf, int32_t* status,

@@ -669,9 +669,32 @@ __device__ __forceinline__ double sc_value(const acro_batch_t& b, int s, int pt,
     return b.sc[b.sys_f_off[s] * 3 + (int64_t)X * ne + i];
 }
 
+// The 17 cross-sections at the quadrature nodes of an energy cell depend on the point's energy grid only, not on the
+// temperature: one table per point, shared by its NT systems (they were 29 % of solve_pdi_kernel's instructions, once per
+// system).  Layout sig[(k * ACRO_NR + r) * n_energy_total + pt_e_off + c]: the lanes of solve_pdi_kernel walk over cells c.
+// Same expressions for the node positions as part (A) of solve_pdi_kernel, which uses the table for its ordinary cells
+// (one piece, not clipped by Emax) and evaluates the others itself.
+__global__ void __launch_bounds__(128) pdi_sigma_kernel(acro_batch_t b, double* __restrict__ sig, acro_params_t p) {
+    const int pt = blockIdx.y;
+    const int ne = b.pt_ne[pt];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ne - 1) return;
+    const double* E = b.e_grid + b.pt_e_off[pt];
+    const double y0 = log(E[c]), y1 = log(E[c + 1]);
+    const double h = 0.5 * (y1 - y0), m = y0 + h;
+    const int nq = p.pdi_cell_order;
+    const double* qx = c_glx + gl_offset(nq);
+    double* out = sig + b.pt_e_off[pt] + c;
+    for (int k = 0; k < nq; ++k) {
+        const double y = fma(h, qx[k], m);
+        const double Ev = fexp(y);
+        for (int r = 0; r < ACRO_NR; ++r) out[(int64_t)(k * ACRO_NR + r) * b.n_energy_total] = sigma_rt(r, Ev, y);
+    }
+}
+
 __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const double* __restrict__ G, double* __restrict__ Fout,
                                                         double* __restrict__ pdi, const double* __restrict__ Kws,
-                                                        acro_params_t p, int smem_stride) {
+                                                        const double* __restrict__ sig, acro_params_t p, int smem_stride) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int s = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -807,6 +830,20 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
             if (kEth[r] <= Elo && !(r == 14 && kink_cell)) open |= 1u << r;
         (void)r_hi;
         if (!open) continue;
+        if (sig && nsub == 1 && hi == y1) {
+            // ordinary cell: node positions are the ones of pdi_sigma_kernel, cross-sections from the point's table
+            const double h = 0.5 * (y1 - y0), m = y0 + h;
+            const double* sc = sig + b.pt_e_off[pt] + c;
+#pragma unroll 1
+            for (int k = 0; k < nq; ++k) {
+                const double fe = qw[k] * h * exp(fma(kap, fma(h, qx[k], m), bs));
+#pragma unroll 1
+                for (int r = 0; r < ACRO_NR; ++r)
+                    if (open & (1u << r))
+                        accs[r * 32 + lane] = fma(fe, sc[(int64_t)(k * ACRO_NR + r) * b.n_energy_total], accs[r * 32 + lane]);
+            }
+            continue;
+        }
         for (int q = 0; q < nsub; ++q) {
             const double a = start + piece * (double)q;
             const double h = 0.5 * piece, m = a + h;
@@ -1274,7 +1311,7 @@ cudaError_t launch_count_work(const acro_batch_t& b, const acro_params_t& p, uns
 }
 
 cudaError_t launch_solve_pdi(const acro_batch_t& b, const acro_out_t& o, const DeviceTables& t, const acro_params_t& p,
-                             const double* Kws, cudaStream_t st, LaunchCounters& lc) {
+                             const double* Kws, double* sig, cudaStream_t st, LaunchCounters& lc) {
     (void)t;
     if (b.n_systems == 0) return cudaSuccess;
     const int stride = b.ne_max + max(3 * b.ne_max, b.ne_max + ACRO_NR * 32);   // doubles per warp, see the kernel
@@ -1286,7 +1323,14 @@ cudaError_t launch_solve_pdi(const acro_batch_t& b, const acro_out_t& o, const D
         if (e != cudaSuccess) return e;
     }
     const int blocks = (b.n_systems + wpb - 1) / wpb;
-    solve_pdi_kernel<<<blocks, wpb * 32, smem, st>>>(b, o.G, o.F, o.pdi, Kws, p, stride);
+    if (sig && o.pdi && b.ne_max > 1) {
+        dim3 gs((unsigned)((b.ne_max - 1 + 127) / 128), (unsigned)b.n_points);
+        pdi_sigma_kernel<<<gs, 128, 0, st>>>(b, sig, p);
+        lc.launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    solve_pdi_kernel<<<blocks, wpb * 32, smem, st>>>(b, o.G, o.F, o.pdi, Kws, (o.pdi ? sig : nullptr), p, stride);
     lc.launches++;
     return cudaGetLastError();
 }

@@ -231,8 +231,8 @@ class Engine(object):
 
     @staticmethod
     def point_cost_bytes(ne, nt):
-        """Workspace bytes one point needs (5 K planes + rate work list)."""
-        return nt * (5 * 8 * (ne * (ne + 1) // 2) + 32 * ne) + 4 * nt + 512
+        """Workspace bytes one point needs (5 K planes + rate work list + cross-section table of the pdi cells)."""
+        return nt * (5 * 8 * (ne * (ne + 1) // 2) + 32 * ne) + 4 * nt + 512 + 16 * 17 * 8 * ne
 
     def chunks(self, points, budget=None):
         """Greedy split of the point list so that each chunk's workspace fits the budget."""
