@@ -1,5 +1,8 @@
 // acro_tshared.cuh -- the production kernel builder (kernel_mode = ACRO_KERNELS_FAST): temperature-shared evaluation of
-// the three thermal kernel integrals (kernels_shared_kernel) plus the per-temperature Wien-tail kernel (kernels_wien_kernel).
+// the three thermal kernel integrals plus the per-temperature Wien-tail kernel (kernels_wien_kernel).  This file holds the
+// shared grid, the integration limits, the partial-panel machinery, the Wien kernel and kernels_shared_kernel, the
+// one-thread-per-pair form of the shared kernel (build-time alternative, -DACRO_TS_LANES4=0); the form that ships,
+// kernels_shared4_kernel with four lanes per pair, is in acro_tshared4.cuh and uses the same grid, limits and tables.
 //
 // In   K(E,E',T) ~ int f(E,E',x) * x^p / (e^{x/T} - 1) dlog x   the factor f (the functions F, G of cascade.py:29-80) does
 // not depend on T and the Bose factor does not depend on (E,E').  For all temperatures of one model point whose lower
@@ -16,12 +19,13 @@
 //     the Bose factor (exact for what the panel rule itself resolves), and so is the panel that contains the upper limit
 //     when that is the kinematic one (x_b0 < 200 T); the thermal cut-off 200 T is applied as zeros in the Bose table.
 //
-// kernels_shared_kernel writes all five planes (closed forms included); kernels_wien_kernel then overwrites / adds the
+// The shared kernel writes all five planes (closed forms included); kernels_wien_kernel then overwrites / adds the
 // (pair, T) combinations beyond wien_from * T with its own Gauss-Laguerre rule (acro_fastquad.cuh).  Both evaluate the
 // regime predicates with the same expressions on the same numbers.
 //
 // Tuning constants (each is a -D macro so that tools/gpu_ab_variants.py can time a variant library; values = measured best
 // on the 840-point benchmark slice):
+//   (measured on kernels_shared_kernel; acro_tshared4.cuh inherits TT, PANN, HC, MAXPAN, TOPX and TILES)
 //   ACRO_TS_TT      40   temperatures per tile = accumulators per thread.  One 256-thread block per SM (248 registers) beats
 //                        20 per tile with two blocks by 18 %: f is evaluated once instead of twice for NT = 39/40.
 //   ACRO_TS_PANN    12   nodes per panel (16: same answers to 5e-10, +14 % time; 10: 1.9e-8 and -15 %; 8: 1e-6, rejected)
