@@ -41,7 +41,7 @@ static_assert(kTT % (2 * kLP) == 0 && kPanN % kLP == 0 && kL4N % kL4G == 0,
 #endif
 constexpr int kL4PassesPerBlock = ACRO_L4_PASSES;
 enum { L4_E = 0, L4_EP, L4_XA9, L4_XB9, L4_XA10, L4_XB10, L4_XA11, L4_XB11, L4_CG, L4_CE, L4_BH, L4_PP, L4_C9, L4_C10, L4_I2EP,
-       L4_ACTIVE, L4_NCONST };
+       L4_ACTIVE, L4_TON, L4_NCONST };     // L4_TON: the three first-served temperature indices, packed
 
 __device__ __forceinline__ double node_core(int kind, const PairConst& c, double x, double ix, double y, double x_a, double lna) {
     if (kind == KIND_IC_PHOTON) {
@@ -317,6 +317,27 @@ __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_bat
                 cw[L4_C10 * 32 + lane] = 0.25 * kMe2 / Ep;
                 cw[L4_I2EP * 32 + lane] = 0.5 / Ep;
                 cw[L4_ACTIVE * 32 + lane] = active ? 1.0 : 0.0;
+                // First temperature of the tile that the shared grid serves, per integral: the regime predicates (the
+                // expressions kernels_wien_kernel evaluates on the same numbers) are monotone in T, which ascends with t
+                // -- the Wien kernel's own range search relies on the same fact -- so a bisection replaces 30 predicate
+                // evaluations per lane in the store loops (they were 9 % of the kernel's stall samples).
+                int ton[3];
+#pragma unroll
+                for (int kind = 0; kind < 3; ++kind) {
+                    const double xa = kind == 0 ? L.xa9 : (kind == 1 ? L.xa10 : L.xa11);
+                    const double xb = kind == 0 ? L.xb9 : (kind == 1 ? L.xb10 : L.xb11);
+                    const bool has = active && (kind == KIND_PC_ELECTRON ? xb > xa : xa > 0.0);
+                    const bool reg = has && (deep || xa >= x_bot);
+                    int lo = 0, hi = ntile;           // first t in [0, ntile] with the predicate true
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const bool on = fmin(xb, sT[4 * kTT + mid]) > xa && xa <= sT[5 * kTT + mid] &&
+                                        (kind != KIND_PC_ELECTRON || !(Ep < sT[6 * kTT + mid]));
+                        if (on) hi = mid; else lo = mid + 1;
+                    }
+                    ton[kind] = reg ? lo : kTT;
+                }
+                cw[L4_TON * 32 + lane] = (double)(ton[0] | (ton[1] << 8) | (ton[2] << 16));
             }
             __syncwarp();
             // ---- phase B: four lanes per pair, 8 pairs at a time
@@ -339,7 +360,7 @@ __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_bat
                     const double xa = cw[(L4_XA9 + 2 * kind) * 32 + pp], xb = cw[(L4_XB9 + 2 * kind) * 32 + pp];
                     const bool has = active && (kind == KIND_PC_ELECTRON ? xb > xa : xa > 0.0);
                     const bool act = has && xb > xa && xa <= xa_max && (kind != KIND_PC_ELECTRON || !(Ep < pc_min));
-                    const bool reg = has && (deep || xa >= x_bot);
+                    const int t_on = ((int)cw[L4_TON * 32 + pp] >> (8 * kind)) & 255;
                     shared_integral4(kind, c, xa, xb, g, sx, six, sy, sBq, s_modal, w, q, pw, act, acc);
                     if (!active) continue;
                     if (kind != KIND_PC_ELECTRON) {
@@ -349,8 +370,7 @@ __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_bat
                         for (int tt = 0; tt < kL4T; ++tt) {
                             const int t = tq + tt;
                             if (t < ntile) {
-                                const bool on = reg && fmin(xb, sT[4 * kTT + t]) > xa && xa <= sT[5 * kTT + t];
-                                out[sK[t]] = on ? pre_ic * acc[tt] : 0.0;
+                                out[sK[t]] = t >= t_on ? pre_ic * acc[tt] : 0.0;
                             }
                         }
                     } else {
@@ -363,8 +383,7 @@ __global__ void __launch_bounds__(kL4Threads, 1) kernels_shared4_kernel(acro_bat
                         for (int tt = 0; tt < kL4T; ++tt) {
                             const int t = tq + tt;
                             if (t < ntile) {
-                                const bool on = reg && !(Ep < sT[6 * kTT + t]) && fmin(xb, sT[4 * kTT + t]) > xa && xa <= sT[5 * kTT + t];
-                                const double pair = fma(sT[2 * kTT + t], bh_pair, on ? pre_pc * acc[tt] : 0.0);
+                                const double pair = fma(sT[2 * kTT + t], bh_pair, t >= t_on ? pre_pc * acc[tt] : 0.0);
                                 const int64_t o = sK[t];
                                 out[3 * np + o] = pair;
                                 out[2 * np + o] = fma(sT[kTT + t], compton_e, pair);
