@@ -36,6 +36,9 @@ constexpr int kL4G = 3;                     // node values evaluated together (i
 static_assert(kLP == 2 || kLP == 4, "two or four lanes per pair");
 static_assert(kTT % (2 * kLP) == 0 && kPanN % kLP == 0 && kL4N % kL4G == 0,
               "tile and panel must split over the lanes (LDS.128 needs an even share)");
+#ifndef ACRO_L4_FMA_UNROLL
+#define ACRO_L4_FMA_UNROLL 4              // nodes per trip of the accumulation loop
+#endif
 #ifndef ACRO_L4_PASSES
 #define ACRO_L4_PASSES 2                    // macro-passes (512 pairs each) per block and Bose-table fill
 #endif
@@ -171,7 +174,7 @@ __device__ __forceinline__ void shared_integral4(int kind, const PairConst& c, d
             }
         }
         __syncwarp();                           // weights of all pairs are published
-#pragma unroll 4
+ACRO_UNROLL(ACRO_L4_FMA_UNROLL)
         for (int m = 0; m < kPanN; ++m) {
             const double v = wp[m * kL4PW];
             const double* __restrict__ Bk = sBq + (size_t)(base + m) * kTT;
