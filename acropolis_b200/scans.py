@@ -241,6 +241,12 @@ def _run_points_pipelined(model, param_sets, devices, group, first_group, growth
             target = min(group, growth * target)
     for entry in in_flight:
         finish(entry)
+    # A model holds lists of its own bound methods (get_source_terms, as in the reference): a reference cycle per point that
+    # only the cyclic collector could free.  These models never leave this function, so the cycles are cut here and the
+    # thousands of objects of a call are released by reference counting instead of piling up for a later collection.
+    for m in models:
+        if m is not None:
+            m._sS0 = m._sSc = None
     return np.array(rows)
 
 
