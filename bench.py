@@ -296,9 +296,9 @@ def main_gpu(args):
     solve_bytes = 5 * 8 * pairs       # the solve stage reads every K entry once (G, F, S0 are <1% of that)
     # DRAM traffic and executed-FP64 utilisation of the two kernel-builder kernels from the committed ncu captures of one
     # slice (profiles/r01_ncu_kernels_shared4_kernel.txt, r01_ncu_kernels_wien_kernel.txt): bytes per slice, i.e. per launch pair
-    ncu = {"traffic_bytes_per_launch": 36.56e9 + 9.58e9, "algorithmic_bytes_per_launch": 5 * 8 * pairs / max(k_launches, 1),
-           "fp64_pipe_active_pct": {"kernels_shared4_kernel": 36.5, "kernels_wien_kernel": 54.9},
-           "issue_active_pct": {"kernels_shared4_kernel": 45.3, "kernels_wien_kernel": 65.8},
+    ncu = {"traffic_bytes_per_launch": 36.10e9 + 9.58e9, "algorithmic_bytes_per_launch": 5 * 8 * pairs / max(k_launches, 1),
+           "fp64_pipe_active_pct": {"kernels_shared4_kernel": 38.6, "kernels_wien_kernel": 54.9},
+           "issue_active_pct": {"kernels_shared4_kernel": 46.6, "kernels_wien_kernel": 65.8},
            "source": "profiles/r01_ncu_kernels_shared4_kernel.txt, profiles/r01_ncu_kernels_wien_kernel.txt"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -320,7 +320,7 @@ def main_gpu(args):
                          "share_of_step": stage_ms[1] / stage_ms.sum(), "ncu": ncu},
             "roofline_solve": {"kernel": "solve_pdi_kernel (stage ii+iii)", "bound": "hbm", "achieved": solve_bytes / (stage_ms[2] * 1e-3) / 1e9,
                                "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / (stage_ms[2] * 1e-3) / 1e9 / hbm_peak,
-                               "peak_source": hbm_peak_src, "traffic": 20.78e9,
+                               "peak_source": hbm_peak_src, "traffic": 20.89e9,
                                "traffic_source": "profiles/r01_ncu_solve_pdi_kernel.txt (bytes per slice)"},
             "stage_ms_per_step": {k: float(v / K) for k, v in zip(("rates", "kernels", "solve_pdi", "matrix"), stage_ms)},
             "clocks": clocks}
