@@ -261,7 +261,7 @@ class DecayModel(AbstractModel):
         n_gamma = (2. * zeta3) * (rep([m._sT0 for m in models])**3.) / (pi**2.)
         tau = rep([m._sTau for m in models])
         nd_all = rep([m._sN0a for m in models]) * n_gamma * sf_ratio**3. * np.exp(-delta_t / tau) * (hbar / tau)
-        t_tmax = ii.time(np.array([max(m._sTrg) for m in models]))
+        t_tmax = [ii.time(max(m._sTrg)) for m in models]      # scalar path (memoised): same last bit as point_spec()
         # [sum NT, 3] source arrays of all points at once (same products as _source_arrays), sliced per point below
         braa2, bree = rep([m._sBRaa * 2. for m in models]), rep([m._sBRee for m in models])
         S0_all = np.empty((len(nd_all), 3))

@@ -271,3 +271,24 @@ def test_unpermute_outputs_of_a_cost_sorted_chunk():
     assert np.array_equal(Engine.unpermute("pdi", pdi, perm, ne, nt), np.concatenate(per_sys))
     assert np.array_equal(Engine.unpermute("F", F, perm, ne, nt), np.concatenate(per_f))
     assert np.array_equal(Engine.unpermute("Yf", Yf, None, ne, nt), Yf)
+
+
+def test_vectorised_point_specs_equal_the_per_model_ones():
+    """DecayModel.point_specs (one numpy pass over all points of a scan group) against AbstractModel.point_spec (the
+    reference's per-model source hooks): same grids and source arrays bit for bit, photon and e+e- injection."""
+    from acropolis_b200.models import DecayModel
+    rng = np.random.default_rng(5)
+    models = []
+    for mphi, tau in zip(np.logspace(0.6, 3, 9), 10.**rng.uniform(3, 10, 9)):
+        models.append(DecayModel(float(mphi), float(tau), 10., 1e-10, 0., 1.))
+        models.append(DecayModel(float(mphi), float(tau), 5., 3e-9, 0.7, 0.3))
+    vec = DecayModel.point_specs(models)
+    assert len(vec) == len(models)
+    for m, v in zip(models, vec):
+        s = m.point_spec()
+        assert v.E0 == s.E0 and v.t_at_tmax == s.t_at_tmax and v.sc_mode == s.sc_mode
+        for name in ("E_grid", "T", "S0", "sc", "sc_E"):
+            a, b = getattr(v, name), getattr(s, name)
+            assert (a is None) == (b is None), name
+            if a is not None:
+                assert np.array_equal(np.asarray(a), np.asarray(b)), name
