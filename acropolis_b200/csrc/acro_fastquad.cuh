@@ -201,7 +201,7 @@ __device__ __forceinline__ double integrand_core(const PairConst& c, double x, d
 // int_{x_a}^{x_b} core(x) * x^{P-1} / (pi^2 (e^{x/T}-1)) dx   with P = 2 (IC) or 1 (pair creation)
 template <int KIND, int Q>
 __device__ __forceinline__ double thermal_integral(const PairConst& c, double T, double x_a, double x_b) {
-    const double iT = 1.0 / T;
+    const double iT = frcp(T);
     const double va = x_a * iT;
     if (va > kSteepX && (x_b - x_a) * iT >= kSteepSpan) {
         // Gauss-Laguerre in s = (x - x_a)/T.  The further out on the Wien tail, the smoother the integrand on the scale of
