@@ -269,3 +269,35 @@ def test_full_size_slice_invariants(gpu_engine):
     for k in rng.choice(np.flatnonzero(~trivial), 12, replace=False):
         Yk = DecayModel(par[k]["mphi"], par[k]["tau"], **fixed).run_disintegration()
         assert relerr(Y[k].T, Yk, 1e-30) < 1e-12, par[k]
+
+
+def test_cfg5_resolution_heaviest_point(gpu_engine):
+    """BASELINE config 5 at full size: NE_pd=480, NT_pd=80 and the heaviest point of the scan grid (mphi = 1e3 MeV: NE=1210,
+    NT=160, 117 M (E,E',T) entries, four temperature tiles).  The oracle would need hours here, so the production kernel
+    builder is checked against the library's independent per-(E,E',T) evaluation (kernel_mode = PER_T: Gauss-Legendre /
+    Gauss-Laguerre per entry, no shared grid) and against nucleon-number conservation."""
+    import acropolis_b200.params as params
+    from acropolis_b200.models import DecayModel
+    old = (params.NE_pd, params.NT_pd)
+    try:
+        params.NE_pd, params.NT_pd = 480, 80
+        m = DecayModel(1e3, 1e6, 10., 1e-10, 0., 1.)
+        sp = m.point_spec()
+    finally:
+        params.NE_pd, params.NT_pd = old
+    assert len(sp.E_grid) in (1210, 1211) and len(sp.T) in (159, 160)
+    res = {}
+    try:
+        for mode in (0, 2):
+            params.kernel_mode = mode
+            res[mode] = gpu_engine.run([sp], want=("F", "pdi", "Yf", "status"))
+    finally:
+        params.kernel_mode = 0
+    assert res[0]["status"][0] == 0 and np.all(np.isfinite(res[0]["F"])) and np.all(np.isfinite(res[0]["Yf"]))
+    live = res[2]["F"] > 1e-150
+    assert np.max(np.abs(res[0]["F"][live] / res[2]["F"][live] - 1)) < 1e-6
+    assert relerr(res[0]["pdi"], res[2]["pdi"], 1e-100) < 1e-6
+    assert relerr(res[0]["Yf"], res[2]["Yf"], 1e-30) < 1e-7
+    A = np.array([1., 1., 2., 3., 3., 4., 6., 7., 7.])
+    Y0 = m._sII.bbn_abundances()
+    assert np.max(np.abs((A @ res[0]["Yf"][0]) / (A @ Y0) - 1.)) < 1e-8
