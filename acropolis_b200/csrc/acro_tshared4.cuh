@@ -40,7 +40,7 @@ static_assert(kTT % (2 * kLP) == 0 && kPanN % kLP == 0 && kL4N % kL4G == 0,
 #define ACRO_L4_FMA_UNROLL 4              // nodes per trip of the accumulation loop
 #endif
 #ifndef ACRO_L4_PASSES
-#define ACRO_L4_PASSES 2                    // macro-passes (512 pairs each) per block and Bose-table fill
+#define ACRO_L4_PASSES 4                    // macro-passes (512 pairs each) per block and Bose-table fill (1: 33.5 ms, 2: 31.5, 4: 30.9, 8: 31.1)
 #endif
 constexpr int kL4PassesPerBlock = ACRO_L4_PASSES;
 enum { L4_E = 0, L4_EP, L4_XA9, L4_XB9, L4_XA10, L4_XB10, L4_XA11, L4_XB11, L4_CG, L4_CE, L4_BH, L4_PP, L4_C9, L4_C10, L4_I2EP,
