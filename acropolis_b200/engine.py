@@ -234,6 +234,8 @@ class Engine(object):
         """Workspace bytes one point needs (5 K planes + rate work list + cross-section table of the pdi cells)."""
         return nt * (5 * 8 * (ne * (ne + 1) // 2) + 32 * ne) + 4 * nt + 512 + 16 * 17 * 8 * ne
 
+    MAX_POINTS_PER_CHUNK = 32768     # the kernels index points with blockIdx.y (limit 65535)
+
     def chunks(self, points, budget=None):
         """Greedy split of the point list so that each chunk's workspace fits the budget."""
         if budget is None:
@@ -246,7 +248,7 @@ class Engine(object):
         out, cur, acc = [], [], 0
         for i, p in enumerate(points):
             c = self.point_cost_bytes(len(p.E_grid), len(p.T))
-            if cur and acc + c > budget:
+            if cur and (acc + c > budget or len(cur) >= self.MAX_POINTS_PER_CHUNK):
                 out.append(cur)
                 cur, acc = [], 0
             cur.append(i)

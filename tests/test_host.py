@@ -292,3 +292,17 @@ def test_vectorised_point_specs_equal_the_per_model_ones():
             assert (a is None) == (b is None), name
             if a is not None:
                 assert np.array_equal(np.asarray(a), np.asarray(b)), name
+
+
+def test_chunks_respect_budget_and_point_limit():
+    """Engine.chunks: greedy split by workspace bytes, and never more points per chunk than the kernels' blockIdx.y can
+    index."""
+    from acropolis_b200.engine import Engine, PointSpec
+    eng = object.__new__(Engine)
+    E, T = np.linspace(1.5, 5., 10), np.linspace(1e-3, 2e-3, 2)
+    pts = [PointSpec(5., E, T, np.zeros((2, 3)), 0.)] * 70000
+    ch = eng.chunks(pts, budget=1 << 40)
+    assert [len(c) for c in ch] == [32768, 32768, 4464] and ch[1][0] == 32768
+    one = Engine.point_cost_bytes(10, 2)
+    ch = eng.chunks(pts[:10], budget=3 * one)
+    assert [len(c) for c in ch] == [3, 3, 3, 1]
