@@ -144,6 +144,7 @@ int acro_run_batch(acro_handle_t* h, const acro_batch_t* b, const acro_out_t* o,
                    int32_t stages, void* stream) {
     if (!h || !b || !o) return ACRO_EINVAL;
     if (b->n_points < 0 || b->n_systems < 0) return fail(h, ACRO_EINVAL, "negative counts");
+    if (b->n_points > 65535) return fail(h, ACRO_EINVAL, "n_points > 65535: split the batch (points are indexed by blockIdx.y)");
     if (b->n_points == 0 || b->n_systems == 0) return ACRO_OK;
     if (!b->pt_ne || !b->pt_nt || !b->pt_e_off || !b->pt_sys_off || !b->pt_e0 || !b->pt_t_at_tmax || !b->e_grid ||
         !b->sys_point || !b->sys_T || !b->sys_f_off || !b->sys_k_off || !b->s0)

@@ -99,7 +99,7 @@ typedef struct {
  * Pointers are DEVICE pointers for acro_run_batch and HOST pointers for acro_run_batch_host.
  */
 typedef struct {
-    int32_t n_points;            /* P                                                        */
+    int32_t n_points;            /* P <= 65535 per call (split larger scans into batches)   */
     int32_t n_systems;           /* S                                                        */
     int64_t n_energy_total;      /* sum_p NE_p   (length of e_grid)                          */
     int64_t n_sys_energy_total;  /* sum_s NE_s   (rows of G / F / dense SC)                  */
