@@ -566,11 +566,15 @@ __device__ __forceinline__ void wien_pooled(const acro_batch_t& b, double* __res
                 if (KIND == KIND_IC_PHOTON) { c.c9 = o_c0; }
                 else if (KIND == KIND_IC_ELECTRON) { c.E = o_c0; c.dE = o_c1; c.c10 = o_c2; c.i2Ep = o_c3; }
                 else { c.E = o_c0; c.Ep = o_c1; }
-                const double v = o_pre * thermal_integral<KIND, Q>(c, T, o_xa, ulim);
                 const int64_t o = b.sys_k_off[s0 + t] + o_loc;
+                // the pair-creation integral is ADDED to what the shared kernel left in the gamma -> e planes (closed forms):
+                // request those two values before the integral, not after it (the read-modify-write was 4 % of the samples)
+                double k3 = 0.0, k2 = 0.0;
+                if (KIND == KIND_PC_ELECTRON) { k3 = Kws[3 * np + o]; k2 = Kws[2 * np + o]; }
+                const double v = o_pre * thermal_integral<KIND, Q>(c, T, o_xa, ulim);
                 if (KIND == KIND_IC_PHOTON) Kws[1 * np + o] = v;
                 else if (KIND == KIND_IC_ELECTRON) Kws[4 * np + o] = v;
-                else { Kws[3 * np + o] += v; Kws[2 * np + o] += v; }
+                else { Kws[3 * np + o] = k3 + v; Kws[2 * np + o] = k2 + v; }
             }
         }
     }
