@@ -1021,8 +1021,28 @@ __device__ void expm9(const double* Ain, double* R) {
 __device__ void apply_transfer(const double* A, double t_at_tmax, const double* Y0 /*[9][3]*/, double* expm_out,
                                double* Yf /*[9][3]*/, int* nonfinite) {
     double R[81];
-    expm9(A, R);
-    if (expm_out) for (int i = 0; i < 81; ++i) expm_out[i] = R[i];
+    if (expm_out) {            // the plain exponential, for callers that ask for it (models.py:130)
+        expm9(A, R);
+        for (int i = 0; i < 81; ++i) expm_out[i] = R[i];
+    }
+    // For the abundances the free-neutron decay is folded out of the matrix first.  Neutrons (row/column 0) are never a
+    // target: their column is pure decay into protons and the proton column is empty; the pre-decay below empties the
+    // neutron entry and the post-decay adds whatever neutrons remain to the protons.  So Y_n + Y_p and every other nuclide
+    // do not depend on the neutron lifetime at all, and  exp(A) -> exp(B)  with  B = A, column n := 0, row p += row n,
+    // row n := 0  gives the SAME transfer -- exactly, for any rate -- while ||B||_1 no longer contains rate x time of the
+    // neutron (1.45e9 at tau = 7.5e8 s, ||B||_1 = 2.3e3).  Scaling and squaring doubles the rounding error of the Pade
+    // solve with every squaring, 29 of them for ||A||_1 = 1.45e9: nucleon number drifted by 7.7e-8 (SciPy: 3e-9 on the same
+    // matrix); with the fold the abundances agree with a 60-digit evaluation to 6e-14 (tools/proto/expm_fold_study.py).
+    double B[81];
+    bool foldable = (A[0 * 9 + 0] + A[1 * 9 + 0] == 0.0);
+    for (int i = 2; i < 9; ++i) foldable = foldable && A[i * 9 + 0] == 0.0;
+    for (int i = 0; i < 9; ++i) foldable = foldable && A[i * 9 + 1] == 0.0;
+    for (int i = 0; i < 81; ++i) B[i] = A[i];
+    if (foldable) {
+        for (int i = 0; i < 9; ++i) B[i * 9 + 0] = 0.0;
+        for (int k = 0; k < 9; ++k) { B[1 * 9 + k] += B[0 * 9 + k]; B[0 * 9 + k] = 0.0; }
+    }
+    expm9(B, R);
     const double ef = exp(-t_at_tmax / kTauT);
     bool bad = false;
     for (int c = 0; c < 3; ++c) {

@@ -49,6 +49,28 @@ def _fsr_columns(E_grid, EX):
     return v
 
 
+def _fold_neutron(mat):
+    """mat with the free-neutron decay folded out: column n := 0, row p += row n, row n := 0 (see _neutron_foldable)."""
+    m = np.array(mat, dtype=np.float64)
+    m[:, 0] = 0.
+    m[1, :] += m[0, :]
+    m[0, :] = 0.
+    return m
+
+
+def _neutron_foldable(model, mpdi, mdcy):
+    """True if exp(mpdi+mdcy) may be replaced by exp of the folded matrix inside post-decay x expm x pre-decay without
+    changing the product: neutrons are no target (their column is pure decay into protons, the proton column is empty),
+    the pre-decay empties the neutron entry and the post-decay adds the remaining neutrons to the protons -- so nothing
+    depends on the neutron lifetime, while its rate x time (up to 1e9) is what forces ~29 squarings in expm and costs 8
+    digits of nucleon-number conservation.  Same fold as apply_transfer() in csrc/acro_kernels.cu, so that
+    run_disintegration() and the batched scan path give the same abundances."""
+    if not _hooks_unchanged(model, AbstractModel, ("_pred_matrix", "_postd_matrix")):
+        return False
+    a = np.asarray(mpdi) + np.asarray(mdcy)
+    return bool(a[0, 0] + a[1, 0] == 0. and not a[2:, 0].any() and not a[:, 1].any())
+
+
 class AbstractModel(ABC):
 
     def __init__(self, e0, ii):
@@ -127,6 +149,8 @@ class AbstractModel(ABC):
             out = eng.run([self.point_spec()], want=("mpdi", "mdcy", "status"))
             self._sMatpBuffer = (out["mpdi"][0], out["mdcy"][0])
         mpdi, mdcy = self._sMatpBuffer
+        if _neutron_foldable(self, mpdi, mdcy):
+            mpdi, mdcy = _fold_neutron(mpdi), _fold_neutron(mdcy)
         _, ex = eng.transfer(mpdi, mdcy, 1.0, self._t_at_tmax(), want_expm=True)
         return ex[0]
 
