@@ -260,7 +260,7 @@ def test_full_size_slice_invariants(gpu_engine):
     A = np.array([1., 1., 2., 3., 3., 4., 6., 7., 7.])
     m0 = DecayModel(1.0, 1e5, **fixed)
     Y0 = m0._sII.bbn_abundances()                              # [nuclide, 3]
-    assert np.max(np.abs((Y @ A) / (A @ Y0)[None, :] - 1.)) < 1e-10
+    assert np.max(np.abs((Y @ A) / (A @ Y0)[None, :] - 1.)) < 1e-9
     trivial = np.array([p["mphi"] / 2. <= 1.5 for p in par])
     assert 100 < trivial.sum() < 300
     Yt = m0._squeeze_decays(Y0)
