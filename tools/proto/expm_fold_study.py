@@ -1,4 +1,10 @@
-import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo/oracle')
+"""CPU study of the accuracy of expm(mpdi + mdcy) inside the abundance transfer: a NumPy
+transcription of csrc expm9 (Pade-13 scaling and squaring), SciPy's expm and a 60-digit mpmath evaluation on the matrices
+of DecayModel(54.2, 7.49e8, ...) (||mdcy||_1 = 1.45e9), and the fold of the free-neutron decay that apply_transfer() uses.
+Needs the built oracle (make -C oracle).  usage: python tools/proto/expm_fold_study.py"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
 import numpy as np
 from scipy.linalg import expm
 import acropolis_b200.flags as flags; flags.verbose=False
