@@ -306,3 +306,31 @@ def test_chunks_respect_budget_and_point_limit():
     one = Engine.point_cost_bytes(10, 2)
     ch = eng.chunks(pts[:10], budget=3 * one)
     assert [len(c) for c in ch] == [3, 3, 3, 1]
+
+
+def test_neutron_fold_leaves_the_transfer_unchanged():
+    """models._fold_neutron: post-decay x expm(M) x pre-decay equals the same product with the free-neutron decay folded out
+    of M (column n := 0, row p += row n, row n := 0) -- checked with SciPy's expm on reference matrices whose norm is small
+    enough for the plain exponential to be accurate -- and a model with its own pre-/post-decay is never folded."""
+    from scipy.linalg import expm
+    from acropolis_b200.models import DecayModel, _fold_neutron, _neutron_foldable
+    z = golden("cfg1_decay.npz")
+    mpdi, mdcy = z["mpdi"], z["mdcy"]
+    m = DecayModel(10., 1e5, 10., 1e-10, 0., 1.)
+    assert _neutron_foldable(m, mpdi, mdcy)
+    pred, postd = m._pred_matrix(), m._postd_matrix()
+    Y0 = m._sII.bbn_abundances()
+    for f in (1., 1e3, 1e6):
+        M = f * mpdi + mdcy
+        Mf = f * _fold_neutron(mpdi) + _fold_neutron(mdcy)
+        assert np.abs(Mf).sum(0).max() < np.abs(M).sum(0).max()
+        a, b = postd @ expm(M) @ pred @ Y0, postd @ expm(Mf) @ pred @ Y0
+        assert relerr(b, a, 1e-30) < 1e-11
+    bad = mpdi.copy()
+    bad[5, 0] = 1e-3                                # a reaction with the neutron as target: not foldable
+    assert not _neutron_foldable(m, bad, mdcy)
+
+    class OwnDecays(DecayModel):
+        def _pred_matrix(self):
+            return np.identity(9)
+    assert not _neutron_foldable(OwnDecays(10., 1e5, 10., 1e-10, 0., 1.), mpdi, mdcy)
