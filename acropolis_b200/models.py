@@ -379,6 +379,44 @@ class AnnihilationModel(AbstractModel):
         sc_E = np.column_stack([_fsr_shape(E_grid, self._sE0), np.zeros(len(E_grid)), np.zeros(len(E_grid))])
         return S0, _lib.SC_SEPARABLE, sc, sc_E
 
+    @classmethod
+    def point_specs(cls, models):
+        """Group form for plain AnnihilationModels on one temperature grid (all of them have Tmax = me^2/(11 Emin) and four
+        decades): the table interpolations are done once for the group, the rest is a handful of 80-element array
+        operations per model, in the order of _number_density / _dm_temperature / _sigma_v so that the arrays are bit-equal
+        to the per-model ones (tests/test_host.py)."""
+        if (not models or any(type(m) is not AnnihilationModel for m in models) or len({id(m._sII) for m in models}) != 1
+                or len({m._sTrg for m in models}) != 1):
+            return [m.point_spec() for m in models]
+        ii = models[0]._sII
+        T = temperature_grid(*models[0]._sTrg)
+        sfT = ii.scale_factor(T)
+        T0 = 2.72548 * 8.6173324e-11
+        Tmin = ii.temperature_range()[0] * (1 + 1e-6)
+        sf0 = ii.scale_factor(Tmin) * Tmin / T0
+        cube = (sf0 / sfT)**3.
+        t_tmax = float(ii.time(max(models[0]._sTrg)))
+        nu = (hbar**2.) * (c_si**3.)
+        z = np.zeros_like(T)
+        specs = []
+        for m in models:
+            nd = 8.095894680377574e-35 * m._sOmgh2 * cube / m._sMchi
+            below = T < m._sTkd
+            Tdm = np.where(below, m._sTkd * (ii.scale_factor(m._sTkd) / sfT)**2., T) if np.any(below) else T
+            base = (nd**2.) * (m._sSwave / nu + m._sPwave / nu * (6. * Tdm / m._sMchi))
+            E_grid = energy_grid(m._sE0)
+            half = m._sBRee * .5 * base
+            S0 = np.empty((len(T), 3))
+            S0[:, 0] = m._sBRaa * base
+            S0[:, 1] = S0[:, 2] = half
+            if m._sBRee == 0.:
+                specs.append(PointSpec.trusted(float(m._sE0), E_grid, T, S0, t_tmax))
+            else:
+                sc = np.column_stack([half, z, z])
+                specs.append(PointSpec.trusted(float(m._sE0), E_grid, T, S0, t_tmax, _lib.SC_SEPARABLE, sc,
+                                               _fsr_columns(E_grid, m._sE0)))
+        return specs
+
     def _sigma_v_array(self, T):
         """<sigma v> on an array of temperatures; subclasses with a scalar-only _sigma_v are looped."""
         try:

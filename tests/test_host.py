@@ -334,3 +334,24 @@ def test_neutron_fold_leaves_the_transfer_unchanged():
         def _pred_matrix(self):
             return np.identity(9)
     assert not _neutron_foldable(OwnDecays(10., 1e5, 10., 1e-10, 0., 1.), mpdi, mdcy)
+
+
+def test_annihilation_point_specs_equal_the_per_model_ones():
+    """AnnihilationModel.point_specs (group form) against point_spec(): bit-equal grids and source arrays, s- and p-wave,
+    photon and e+e- channels, kinetic decoupling inside and outside the temperature range."""
+    from acropolis_b200.models import AnnihilationModel
+    models = []
+    for mchi in np.logspace(0.4, 2.5, 5):
+        models.append(AnnihilationModel(float(mchi), 1e-25, 0., 1., 1., 0.))
+        models.append(AnnihilationModel(float(mchi), 0., 3e-21, 1e-3, 0.4, 0.6, omegah2=0.1))
+        models.append(AnnihilationModel(float(mchi), 2e-26, 1e-22, 1e-7, 0., 1.))
+    vec = AnnihilationModel.point_specs(models)
+    assert len(vec) == len(models)
+    for m, v in zip(models, vec):
+        s = m.point_spec()
+        assert v.E0 == s.E0 and v.t_at_tmax == s.t_at_tmax and v.sc_mode == s.sc_mode
+        for name in ("E_grid", "T", "S0", "sc", "sc_E"):
+            a, b = getattr(v, name), getattr(s, name)
+            assert (a is None) == (b is None), name
+            if a is not None:
+                assert np.array_equal(np.asarray(a), np.asarray(b)), name
