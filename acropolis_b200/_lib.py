@@ -7,12 +7,16 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACROPOLIS_B200_LIB") or os.path.join(_HERE, "libacropolis_b200.so")   # env override: kernel A/B builds
+# the same sources with -DACRO_CROSSCHECK: adds the per-(E,E',T) cross-check modes (kernel_mode PLAIN_GL / PER_T) for the tests
+XCHECK_LIB_PATH = os.path.join(_HERE, "libacropolis_b200_xcheck.so")
 
 NX, NY, NR, NK = 3, 9, 17, 5
 STAGE_RATES, STAGE_KERNELS, STAGE_SOLVE, STAGE_MATRIX, STAGE_ALL = 1, 2, 4, 8, 15
 ST_NONFINITE, ST_T_OUTSIDE, ST_DIRECT_RATE, ST_E0_ABOVE_GEV = 1, 2, 4, 8
 SC_NONE, SC_SEPARABLE, SC_DENSE = 0, 1, 2
-KERNELS_FAST, KERNELS_PLAIN_GL = 0, 1
+KERNELS_FAST, KERNELS_PLAIN_GL, KERNELS_PER_T = 0, 1, 2
+ABI_VERSION = 3
+KERNEL_SPLIT_NAMES = ("pair_closed_forms_kernel", "kernels_mma_kernel", "kernels_wien_kernel")
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -30,15 +34,17 @@ class Tables(C.Structure):
 class Params(C.Structure):
     _fields_ = [("quad_order", C.c_int32), ("pdi_cell_order", C.c_int32), ("Emin", C.c_double),
                 ("approx_zero", C.c_double), ("Ephb_T_max", C.c_double), ("E_EC_max", C.c_double),
-                ("use_db", C.c_int32), ("kernel_mode", C.c_int32), ("wien_from", C.c_double)]
+                ("use_db", C.c_int32), ("kernel_mode", C.c_int32), ("wien_from", C.c_double),
+                ("universal", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Batch(C.Structure):
     _fields_ = [("n_points", C.c_int32), ("n_systems", C.c_int32), ("n_energy_total", C.c_int64),
-                ("n_sys_energy_total", C.c_int64), ("n_pairs_total", C.c_int64), ("ne_max", C.c_int32),
+                ("n_sys_energy_total", C.c_int64), ("n_pairs_total", C.c_int64), ("n_pairs_points", C.c_int64),
+                ("ne_max", C.c_int32),
                 ("nt_max", C.c_int32), ("sc_mode", C.c_int32), ("reserved", C.c_int32),
                 ("pt_ne", C.c_void_p), ("pt_nt", C.c_void_p), ("pt_e_off", C.c_void_p), ("pt_sys_off", C.c_void_p),
-                ("pt_e0", C.c_void_p), ("pt_t_at_tmax", C.c_void_p), ("e_grid", C.c_void_p),
+                ("pt_pair_off", C.c_void_p), ("pt_e0", C.c_void_p), ("pt_t_at_tmax", C.c_void_p), ("e_grid", C.c_void_p),
                 ("sys_point", C.c_void_p), ("sys_T", C.c_void_p), ("sys_f_off", C.c_void_p), ("sys_k_off", C.c_void_p),
                 ("s0", C.c_void_p), ("sc", C.c_void_p), ("sc_E", C.c_void_p)]
 
@@ -53,18 +59,19 @@ EXPORTS = ("acro_abi_version", "acro_default_params", "acro_create", "acro_destr
            "acro_transfer_batch", "acro_total_rates", "acro_measure_fp64_peak", "acro_last_stage_ms", "acro_last_kernel_split_ms", "acro_launch_count",
            "acro_count_work")
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Load the shared library (once) and declare the prototypes; raises if it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(variant="product"):
+    """Load the shared library (once per variant) and declare the prototypes; raises if it has not been built.
+    ``variant`` = "product" (what ships) or "xcheck" (test build with the cross-check kernel modes)."""
+    if variant in _libs:
+        return _libs[variant]
+    path = LIB_PATH if variant == "product" else XCHECK_LIB_PATH
+    if not os.path.exists(path):
         raise ImportError("acropolis_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; "
-                          "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+                          "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % path)
+    lib = C.CDLL(path)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.acro_abi_version.restype = C.c_int
     lib.acro_default_params.argtypes = [C.POINTER(Params)]
@@ -84,13 +91,13 @@ def load():
     lib.acro_total_rates.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.acro_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.acro_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
-    lib.acro_last_kernel_split_ms.argtypes = [vp, C.POINTER(C.c_float * 2)]
+    lib.acro_last_kernel_split_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]
     lib.acro_count_work.argtypes = [vp, C.POINTER(Batch), C.POINTER(C.c_int64 * 4), vp]
     lib.acro_launch_count.argtypes = [vp]
     lib.acro_launch_count.restype = i64
     for name in EXPORTS:
         getattr(lib, name)
-    if lib.acro_abi_version() != 2:
-        raise ImportError("acropolis_b200: ABI version mismatch in %s" % LIB_PATH)
-    _lib = lib
+    if lib.acro_abi_version() != ABI_VERSION:
+        raise ImportError("acropolis_b200: ABI version mismatch in %s" % path)
+    _libs[variant] = lib
     return lib

@@ -12,6 +12,7 @@ SRC = [os.path.join(HERE, "csrc", f) for f in ("acro_kernels.cu", "acro_api.cu")
 DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))] + \
     [os.path.join(HERE, "..", "include", "acropolis_b200.h")]
 OUT = os.path.join(HERE, "libacropolis_b200.so")
+OUT_XCHECK = os.path.join(HERE, "libacropolis_b200_xcheck.so")   # same sources + the cross-check kernel modes (tests only)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -23,11 +24,18 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
-def up_to_date():
-    if not os.path.exists(OUT):
+def up_to_date(out=OUT):
+    if not os.path.exists(out):
         return False
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     return all(os.path.getmtime(d) <= t for d in DEPS)
+
+
+def build_xcheck_library(force=False):
+    """The test build: product sources with -DACRO_CROSSCHECK (kernel_mode PLAIN_GL / PER_T available)."""
+    if not force and up_to_date(OUT_XCHECK):
+        return OUT_XCHECK
+    return build_library(force=True, out=OUT_XCHECK, defines=("-DACRO_CROSSCHECK",))
 
 
 def build_library(force=False, verbose=False, out=None, defines=()):
@@ -46,3 +54,4 @@ def build_library(force=False, verbose=False, out=None, defines=()):
 
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_xcheck_library(force="--force" in sys.argv))

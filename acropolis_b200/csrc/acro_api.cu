@@ -51,6 +51,7 @@ void acro_default_params(acro_params_t* p) {
     p->use_db = 1;
     p->kernel_mode = ACRO_KERNELS_FAST;
     p->wien_from = 7.38905609893065;
+    p->universal = 0;
 }
 
 static int check_params(acro_handle* h, const acro_params_t* p) {
@@ -58,6 +59,10 @@ static int check_params(acro_handle* h, const acro_params_t* p) {
         return fail(h, ACRO_EINVAL, "quad_order must be 16, 32, 64 or 96");
     if (!(p->pdi_cell_order == 8 || p->pdi_cell_order == 16)) return fail(h, ACRO_EINVAL, "pdi_cell_order must be 8 or 16");
     if (!(p->kernel_mode == ACRO_KERNELS_FAST || p->kernel_mode == ACRO_KERNELS_PLAIN_GL || p->kernel_mode == ACRO_KERNELS_PER_T)) return fail(h, ACRO_EINVAL, "bad kernel_mode");
+#ifndef ACRO_CROSSCHECK
+    if (p->kernel_mode != ACRO_KERNELS_FAST)
+        return fail(h, ACRO_EINVAL, "kernel_mode PLAIN_GL / PER_T exist only in the cross-check build (libacropolis_b200_xcheck.so, -DACRO_CROSSCHECK)");
+#endif
     if (!(p->wien_from >= 2.718281828459045 && p->wien_from <= 7.38905609893066)) return fail(h, ACRO_EINVAL, "wien_from must lie in [e, e^2]");
     if (!(p->Emin > 0 && p->approx_zero > 0 && p->Ephb_T_max > 0 && p->E_EC_max > 0)) return fail(h, ACRO_EINVAL, "bad params");
     return ACRO_OK;
@@ -96,7 +101,7 @@ int acro_create(acro_handle_t** out, int device, const acro_tables_t* t, const a
     d.eta = t->eta; d.Yp = t->Y0[1 * 3 + 0]; d.YHe4 = t->Y0[5 * 3 + 0];
     for (int i = 0; i < 27; ++i) d.Y0[i] = t->Y0[i];
     for (int i = 0; i < 5; ++i) cudaEventCreate(&h->ev[i]);
-    cudaEventCreate(&h->lc.split);
+    cudaEventCreate(&h->lc.split[0]); cudaEventCreate(&h->lc.split[1]);
     *out = h;
     return ACRO_OK;
 }
@@ -106,7 +111,7 @@ int acro_destroy(acro_handle_t* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_ratedb); cudaFree(h->d_cosmo_lT); cudaFree(h->d_cosmo_ld);
     for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    if (h->lc.split) cudaEventDestroy(h->lc.split);
+    for (int i = 0; i < 2; ++i) if (h->lc.split[i]) cudaEventDestroy(h->lc.split[i]);
     delete h;
     return ACRO_OK;
 }
@@ -121,13 +126,15 @@ int acro_set_params(acro_handle_t* h, const acro_params_t* p) {
     return ACRO_OK;
 }
 
-// workspace layout: [5 K planes][direct-rate items][cross-section table of the pdi cells][item counter (256 B)][per-system status]
+// workspace layout: [5 K planes][pair closed forms][direct-rate items][cross-section table of the pdi cells][item counter
+// (256 B)][per-system status]
 static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
-struct WsLayout { int64_t k, items, sig, counter, status, total; };
+struct WsLayout { int64_t k, closed, items, sig, counter, status, total; };
 static WsLayout ws_layout(const acro_batch_t* b) {
     WsLayout w;
     w.k = 0;
-    w.items = align256((int64_t)ACRO_NK * b->n_pairs_total * (int64_t)sizeof(double));
+    w.closed = align256((int64_t)ACRO_NK * b->n_pairs_total * (int64_t)sizeof(double));
+    w.items = w.closed + align256((int64_t)3 * b->n_pairs_points * (int64_t)sizeof(double));
     w.sig = w.items + align256(b->n_sys_energy_total * (int64_t)sizeof(DirectRateItem));
     w.counter = w.sig + align256((int64_t)16 * ACRO_NR * b->n_energy_total * (int64_t)sizeof(double));   // up to 16 nodes per cell
     w.status = w.counter + 256;
@@ -147,8 +154,9 @@ int acro_run_batch(acro_handle_t* h, const acro_batch_t* b, const acro_out_t* o,
     if (b->n_points > 65535) return fail(h, ACRO_EINVAL, "n_points > 65535: split the batch (points are indexed by blockIdx.y)");
     if (b->n_points == 0 || b->n_systems == 0) return ACRO_OK;
     if (!b->pt_ne || !b->pt_nt || !b->pt_e_off || !b->pt_sys_off || !b->pt_e0 || !b->pt_t_at_tmax || !b->e_grid ||
-        !b->sys_point || !b->sys_T || !b->sys_f_off || !b->sys_k_off || !b->s0)
+        !b->sys_point || !b->sys_T || !b->sys_f_off || !b->sys_k_off || !b->s0 || !b->pt_pair_off)
         return fail(h, ACRO_EINVAL, "acro_run_batch: null batch array");
+    if ((b->n_pairs_total & 3) != 0) return fail(h, ACRO_EINVAL, "n_pairs_total must be a multiple of 4 (every system's plane block is padded to 4 entries)");
     if (b->sc_mode != ACRO_SC_NONE && !b->sc) return fail(h, ACRO_EINVAL, "sc_mode set but sc is NULL");
     if (b->sc_mode == ACRO_SC_SEPARABLE && !b->sc_E) return fail(h, ACRO_EINVAL, "separable sc needs sc_E");
     if (b->ne_max < 2) return fail(h, ACRO_EINVAL, "ne_max < 2");
@@ -170,7 +178,8 @@ int acro_run_batch(acro_handle_t* h, const acro_batch_t* b, const acro_out_t* o,
         CU(h, launch_direct_rates(h->tables, h->params, o->G, items, counter, b->n_sys_energy_total, st, h->lc));
     }
     CU(h, cudaEventRecord(h->ev[1], st));
-    if (stages & ACRO_STAGE_KERNELS) CU(h, launch_kernels(*b, h->tables, h->params, Kws, st, h->lc));
+    if ((stages & ACRO_STAGE_KERNELS) && !h->params.universal)
+        CU(h, launch_kernels(*b, h->tables, h->params, Kws, (double*)(base + w.closed), st, h->lc));
     CU(h, cudaEventRecord(h->ev[2], st));
     if (stages & ACRO_STAGE_SOLVE) CU(h, launch_solve_pdi(*b, *o, h->tables, h->params, Kws, (double*)(base + w.sig), st, h->lc));
     CU(h, cudaEventRecord(h->ev[3], st));
@@ -208,12 +217,13 @@ int acro_last_stage_ms(acro_handle_t* h, float ms[4]) {
     return ACRO_OK;
 }
 
-int acro_last_kernel_split_ms(acro_handle_t* h, float ms[2]) {
+int acro_last_kernel_split_ms(acro_handle_t* h, float ms[3]) {
     if (!h || !ms) return ACRO_EINVAL;
     if (!h->ev_valid || !h->lc.split_valid) return fail(h, ACRO_EINVAL, "the production kernel builder has not run on this handle");
     CU(h, cudaEventSynchronize(h->ev[2]));
-    CU(h, cudaEventElapsedTime(&ms[0], h->ev[1], h->lc.split));
-    CU(h, cudaEventElapsedTime(&ms[1], h->lc.split, h->ev[2]));
+    CU(h, cudaEventElapsedTime(&ms[0], h->ev[1], h->lc.split[0]));
+    CU(h, cudaEventElapsedTime(&ms[1], h->lc.split[0], h->lc.split[1]));
+    CU(h, cudaEventElapsedTime(&ms[2], h->lc.split[1], h->ev[2]));
     return ACRO_OK;
 }
 
@@ -238,13 +248,15 @@ int acro_run_batch_host(acro_handle_t* h, const acro_batch_t* hb, const acro_out
     CU(h, cudaSetDevice(h->device));
     cudaStream_t st = nullptr;
     const size_t P = hb->n_points, S = hb->n_systems, NEt = hb->n_energy_total, NF = hb->n_sys_energy_total;
-    DevBuf pt_ne, pt_nt, pt_e_off, pt_sys_off, pt_e0, pt_tt, e_grid, sys_point, sys_T, sys_f_off, sys_k_off, s0, sc, sc_E;
+    DevBuf pt_ne, pt_nt, pt_e_off, pt_sys_off, pt_pair_off, pt_e0, pt_tt, e_grid, sys_point, sys_T, sys_f_off, sys_k_off, s0, sc, sc_E;
     DevBuf G, F, pdi, mpdi, mdcy, Yf, status, ws;
     acro_batch_t db = *hb;
     CU(h, pt_ne.upload(hb->pt_ne, P * 4, st));           db.pt_ne = (const int32_t*)pt_ne.p;
     CU(h, pt_nt.upload(hb->pt_nt, P * 4, st));           db.pt_nt = (const int32_t*)pt_nt.p;
     CU(h, pt_e_off.upload(hb->pt_e_off, P * 8, st));     db.pt_e_off = (const int64_t*)pt_e_off.p;
     CU(h, pt_sys_off.upload(hb->pt_sys_off, P * 4, st)); db.pt_sys_off = (const int32_t*)pt_sys_off.p;
+    if (!hb->pt_pair_off) return fail(h, ACRO_EINVAL, "acro_run_batch_host: pt_pair_off is NULL");
+    CU(h, pt_pair_off.upload(hb->pt_pair_off, P * 8, st)); db.pt_pair_off = (const int64_t*)pt_pair_off.p;
     CU(h, pt_e0.upload(hb->pt_e0, P * 8, st));           db.pt_e0 = (const double*)pt_e0.p;
     CU(h, pt_tt.upload(hb->pt_t_at_tmax, P * 8, st));    db.pt_t_at_tmax = (const double*)pt_tt.p;
     CU(h, e_grid.upload(hb->e_grid, NEt * 8, st));       db.e_grid = (const double*)e_grid.p;

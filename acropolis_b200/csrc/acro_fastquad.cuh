@@ -199,11 +199,13 @@ __device__ __forceinline__ double integrand_core(const PairConst& c, double x, d
 }
 
 // int_{x_a}^{x_b} core(x) * x^{P-1} / (pi^2 (e^{x/T}-1)) dx   with P = 2 (IC) or 1 (pair creation)
-template <int KIND, int Q>
+// STEEP_ONLY: the caller guarantees x_a > e T (kernels_wien_kernel: x_a > wien_from T, wien_from >= e), so the plain
+// Gauss-Legendre branch is not instantiated
+template <int KIND, int Q, bool STEEP_ONLY = false>
 __device__ __forceinline__ double thermal_integral(const PairConst& c, double T, double x_a, double x_b) {
     const double iT = frcp(T);
     const double va = x_a * iT;
-    if (va > kSteepX && (x_b - x_a) * iT >= kSteepSpan) {
+    if ((STEEP_ONLY || va > kSteepX) && (x_b - x_a) * iT >= kSteepSpan) {
         // Gauss-Laguerre in s = (x - x_a)/T.  The further out on the Wien tail, the smoother the integrand on the scale of
         // the weight, so the order follows va = x_a/T (worst relative error of each band in tools/proto, all <= 4e-10):
         //   va in (e, e^1.5]: 24   (e^1.5, e^2]: 16   (e^2, e^2.5]: 12   (e^2.5, e^3]: 8   (e^3, e^4]: 6   > e^4: 4
@@ -228,7 +230,7 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
         }
         return sum * T * Ea * (1.0 / kPi2);
     }
-    if (va > kSteepX) {
+    if (STEEP_ONLY || va > kSteepX) {
         // Wien tail with a short span S = (x_b - x_a)/T < 32: Gauss-Legendre (32 nodes) in s on [0, S] with the explicit
         // weight e^{-s}; no logarithmic variable needed because the integrand varies on the scale x_a/T > e.
         const double S = (x_b - x_a) * iT;

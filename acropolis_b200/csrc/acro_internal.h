@@ -30,7 +30,7 @@ struct DirectRateItem {
 
 struct LaunchCounters {
     int64_t launches = 0;
-    cudaEvent_t split = nullptr;   // recorded between the two launches of the production kernel builder
+    cudaEvent_t split[2] = {nullptr, nullptr};   // recorded between the three launches of the production kernel builder
     bool split_valid = false;
 };
 
@@ -40,7 +40,7 @@ cudaError_t launch_rates(const acro_batch_t& b, const acro_out_t& o, const Devic
                          DirectRateItem* items, int* item_count, int* status_sys, cudaStream_t st, LaunchCounters& lc);
 cudaError_t launch_direct_rates(const DeviceTables& t, const acro_params_t& p, double* G, const DirectRateItem* items,
                                 const int* item_count, int64_t max_items, cudaStream_t st, LaunchCounters& lc);
-cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const acro_params_t& p, double* Kws,
+cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const acro_params_t& p, double* Kws, double* closed,
                            cudaStream_t st, LaunchCounters& lc);
 cudaError_t launch_count_work(const acro_batch_t& b, const acro_params_t& p, unsigned long long* out, cudaStream_t st,
                               LaunchCounters& lc);

@@ -2,11 +2,14 @@
 //
 //   rates_kernel        thread per (system, E_i)        G[3,NE]: closed forms + rates.db bilinear interpolation
 //   direct_rates_kernel warp per out-of-table (E,T)     the two 2-D rate integrals the reference does with dblquad
-//   kernels_shared_kernel / kernels_wien_kernel         the production kernel builder (acro_tshared.cuh): five K planes,
-//                                                       closed forms + three Planck-weighted integrals on a
-//                                                       temperature-shared grid / Gauss-Laguerre on the Wien tail
-//   kernels_kernel      thread per (system, E_i, E_j>=i) cross-check modes: fixed-order Gauss-Legendre in log(eps_bar)
-//                                                       per (E,E',T) (PLAIN_GL with the reference's F/G, PER_T reduced)
+//   pair_closed_forms_kernel / kernels_mma_kernel / kernels_wien_kernel
+//                                                       the production kernel builder (acro_tmma.cuh, acro_tshared.cuh): five
+//                                                       K planes, closed forms + three Planck-weighted integrals on a
+//                                                       temperature-shared grid contracted with DMMA / Gauss-Laguerre on
+//                                                       the Wien tail
+//   kernels_kernel      thread per (system, E_i, E_j>=i) cross-check modes, only with -DACRO_CROSSCHECK (the test build):
+//                                                       fixed-order Gauss-Legendre in log(eps_bar) per (E,E',T)
+//                                                       (PLAIN_GL with the reference's F/G, PER_T reduced)
 //   solve_pdi_kernel    warp per system                 back-substitution of the 3-species cascade equation,
 //                                                       fused with the 17 sigma(E)*F(E) rate integrals
 //   matrix_kernel       warp per point                  exact piecewise T-integral, 9x9 expm, decay matrices, Yf
@@ -41,13 +44,8 @@ __host__ __device__ constexpr int gl_offset(int order) {
 
 }  // namespace acro
 #include "acro_fastquad.cuh"
-// 1: kernels_shared4_kernel (four lanes per pair, acro_tshared4.cuh), the production form; 0: kernels_shared_kernel (one
-// thread per pair, acro_tshared.cuh), kept as the build-time alternative it was derived from and is checked against
-#ifndef ACRO_TS_LANES4
-#define ACRO_TS_LANES4 1
-#endif
 #include "acro_tshared.cuh"
-#include "acro_tshared4.cuh"
+#include "acro_tmma.cuh"
 namespace acro {
 
 static void gauss_laguerre(int n, double* x, double* w) {   // alpha = 0; Newton on L_n with the classic initial guesses
@@ -332,6 +330,7 @@ __global__ void __launch_bounds__(128) direct_rates_kernel(double* __restrict__ 
 // The thermal integrals run over log(eps_bar) with a Q-point Gauss-Legendre rule (Q = quad_order); the
 // reference uses adaptive QAGS at epsrel=1e-3, which GL-64 reproduces to <=1.4e-10.
 // ------------------------------------------------------------------------------------------------------------
+#ifdef ACRO_CROSSCHECK
 template <int Q>
 __device__ __forceinline__ double integral_ic_photon(double E, double Ep, double T, double llim, double ulim) {
     const double a = log(llim), b = log(ulim);
@@ -497,6 +496,7 @@ __global__ void __launch_bounds__(128, ACRO_KK_MINBLOCKS) kernels_kernel(acro_ba
     const int64_t loc = tid - b.sys_k_off[s];
     const int pt = b.sys_point[s];
     const int ne = b.pt_ne[pt];
+    if (loc >= (int64_t)ne * (ne + 1) / 2) return;   // pad entries between systems (sector alignment)
     // invert loc = i*ne - i(i-1)/2 + (j-i)
     const double tn = 2.0 * ne + 1.0;
     int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
@@ -528,6 +528,8 @@ __global__ void __launch_bounds__(128, ACRO_KK_MINBLOCKS) kernels_kernel(acro_ba
     Kws[4 * np + tid] = k.ee;
 }
 
+#endif  // ACRO_CROSSCHECK
+
 // Counts, for the roofline's algorithmic-work figure, the (system, i, j>=i) pairs and how many of them
 // have a non-empty integration range for each of the three thermal integrals -- the same limit tests as
 // eval_kernels, no quadrature.  out[0..3] = pairs, N_a9 (e->gamma), N_a10 (e->e), N_a11 (gamma->e).
@@ -539,25 +541,26 @@ __global__ void __launch_bounds__(128) count_work_kernel(acro_batch_t b, unsigne
         const int64_t loc = tid - b.sys_k_off[s];
         const int pt = b.sys_point[s];
         const int ne = b.pt_ne[pt];
+        const bool pad = loc >= (int64_t)ne * (ne + 1) / 2;     // pad entries between systems (sector alignment)
         const double tn = 2.0 * ne + 1.0;
-        int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+        int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)(pad ? 0 : loc))));
         i = max(0, min(i, ne - 1));
         while (i > 0 && tri_row_off(i, ne) > loc) --i;
         while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
         const int j = i + (int)(loc - tri_row_off(i, ne));
         const double* eg = b.e_grid + b.pt_e_off[pt];
         const double E = eg[i], Ep = eg[j], T = b.sys_T[s], xmax = p.Ephb_T_max * T;
-        cp = 1;
-        if (!(Ep < E + kMe)) {
+        cp = pad ? 0 : 1;
+        if (!pad && !(Ep < E + kMe)) {
             const double llim = 0.25 * kMe2 * E / (Ep * Ep - Ep * E);
             c9 = fmin(fmin(E, Ep - kMe2 / (4.0 * Ep)), xmax) > llim;
         }
-        if (E != Ep) {
+        if (!pad && E != Ep) {
             const double pf = 0.25 * kMe2 / Ep - E, qf = 0.25 * kMe2 * (Ep - E) / Ep;
             const double sq = sqrt((0.5 * pf) * (0.5 * pf) - qf);
             c10 = fmin(fmin(-0.5 * pf + sq, Ep - kMe2 / (4.0 * Ep)), xmax) > (-0.5 * pf - sq);
         }
-        if (!(Ep < kMe2 / (50.0 * T))) {
+        if (!pad && !(Ep < kMe2 / (50.0 * T))) {
             const double dE = Ep - E, rt = sqrt(E * E - kMe2), den = 4.0 * Ep * dE + kMe2;
             const double z1 = Ep * (kMe2 - 2.0 * dE * (rt - E)) / den, z2 = Ep * (kMe2 + 2.0 * dE * (rt + E)) / den;
             c11 = fmin(fmin(z2, Ep), xmax) > fmax(kMe2 / Ep, z1);
@@ -716,6 +719,23 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
     const double dy = log(E[top] / p.Emin) / (double)(ne - 1);
     double* fo = Fout ? Fout + b.sys_f_off[s] * 3 : nullptr;
 
+    if (p.universal) {
+        // flags.universal (cascade.py:774-812): F_gamma(E) = SN K0 (EX/E)^{3/2 | 2} / Gamma_gamma(E,T) below / above EX =
+        // me^2/(80T), zero (floored) above 1.05 EC with EC = me^2/(22T); no cascade equation.  Leptons are not defined.
+        const double EC = kMe2 / (22.0 * T), EX = kMe2 / (80.0 * T);
+        const double K0u = b.pt_e0[pt] / ((EX * EX) * (2.0 + log(EC / EX)));
+        const double SN = S0[0] + S0[1] + S0[2];
+        for (int i = lane; i < ne; i += 32) {
+            const double Ei = E[i];
+            double F = 0.0;
+            if (Ei < EX) F = SN * K0u * pow(EX / Ei, 1.5) / g[i];
+            else if (Ei <= (1.0 + 5e-2) * EC) F = SN * K0u * pow(EX / Ei, 2.0) / g[i];
+            F = fmax(F, p.approx_zero);
+            lnF[i] = log(F);
+            if (fo) { fo[i] = F; fo[ne + i] = p.approx_zero; fo[2 * ne + i] = p.approx_zero; }
+        }
+        __syncwarp();
+    } else {
     // --- top row (cascade.py:194-198)
     {
         const int64_t r = tri_row_off(top, ne);
@@ -791,6 +811,7 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
         }
         __syncwarp();
     }
+    }   // !universal
     if (!pdi) return;
     for (int i = lane; i < ne; i += 32) lnE[i] = log(E[i]);     // wF is dead from here on
     __syncwarp();
@@ -798,7 +819,7 @@ __global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const do
     // --- photodisintegration rates (nucl.py:398-467)
     const double E0 = b.pt_e0[pt];
     const double EC = kMe2 / (22.0 * T);
-    const double Emax = fmin(E0, p.E_EC_max * EC);
+    const double Emax = p.universal ? fmin(E0, EC) : fmin(E0, p.E_EC_max * EC);    // nucl.py:399-402, :420-422
     const double lnEmax = log(Emax);
     const int nq = p.pdi_cell_order;   // 8 or 16
     const double* qx = c_glx + gl_offset(nq);
@@ -1221,9 +1242,10 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
 // launchers
 // ------------------------------------------------------------------------------------------------------------
 static int sm_count() {
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
-    return n;
+    int n = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
 }
 
 cudaError_t launch_rates(const acro_batch_t& b, const acro_out_t& o, const DeviceTables& t, const acro_params_t& p,
@@ -1247,12 +1269,34 @@ cudaError_t launch_direct_rates(const DeviceTables& t, const acro_params_t& p, d
     return cudaGetLastError();
 }
 
-cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const acro_params_t& p, double* Kws,
+cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const acro_params_t& p, double* Kws, double* closed,
                            cudaStream_t st, LaunchCounters& lc) {
     lc.split_valid = false;
     if (b.n_pairs_total == 0) return cudaSuccess;
-    const int64_t blocks = (b.n_pairs_total + 127) / 128;
-    const unsigned g = (unsigned)blocks;
+    if (p.kernel_mode == ACRO_KERNELS_FAST) {   // the production kernel builder: all five planes
+        const int64_t tri_max = (int64_t)b.ne_max * (b.ne_max + 1) / 2;
+        const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT + (kTileScalars + 1) * kTT +
+                                              2 * kLogTab + kPanN * kPanN + (size_t)kMmWarps * MM_NCONST * 32);
+        const int64_t passes_max = (tri_max + kMmPairs - 1) / kMmPairs;
+        dim3 grid((unsigned)((passes_max + kMmPassesPerBlock - 1) / kMmPassesPerBlock), (unsigned)b.n_points);
+        // function attributes are per device (each primary context has its own CUfunction): set before every launch
+        cudaError_t e = cudaFuncSetAttribute(kernels_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        dim3 gp((unsigned)((tri_max + 127) / 128), (unsigned)b.n_points);
+        pair_closed_forms_kernel<<<gp, 128, 0, st>>>(b, closed);
+        lc.launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (lc.split[0]) cudaEventRecord(lc.split[0], st);
+        kernels_mma_kernel<<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p);
+        lc.launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (lc.split[1]) lc.split_valid = cudaEventRecord(lc.split[1], st) == cudaSuccess;
+        kernels_wien_kernel<64><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
+        lc.launches++;
+        return cudaGetLastError();
+    }
+#ifdef ACRO_CROSSCHECK
+    const unsigned g = (unsigned)((b.n_pairs_total + 127) / 128);
     if (p.kernel_mode == ACRO_KERNELS_PLAIN_GL) {
         switch (p.quad_order) {
             case 16: kernels_kernel<16, false><<<g, 128, 0, st>>>(b, Kws, t, p); break;
@@ -1261,64 +1305,16 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
             default: kernels_kernel<64, false><<<g, 128, 0, st>>>(b, Kws, t, p); break;
         }
     } else {
-        if (p.kernel_mode == ACRO_KERNELS_FAST) {   // the production kernel builder (acro_tshared.cuh): all five planes
-            const int64_t tri_max = (int64_t)b.ne_max * (b.ne_max + 1) / 2;
-            const int64_t tiles_max = (tri_max + kSharedThreads - 1) / kSharedThreads;
-            dim3 grid((unsigned)((tiles_max + kTilesPerBlock - 1) / kTilesPerBlock), (unsigned)b.n_points);
-            const size_t smem_tables = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT +
-                                                         (kTileScalars + 1) * kTT + (ACRO_FQ_LOGTAB ? 2 * kLogTab : 0));
-            cudaError_t e = cudaSuccess;
-#if ACRO_TS_LANES4
-            const size_t smem = smem_tables + sizeof(double) * (kPanN * kPanN + (size_t)kL4Warps * kPanN * kL4PW +
-                                                                (size_t)kL4Warps * L4_NCONST * 32);
-            const int64_t passes_max = (tri_max + kL4Pairs - 1) / kL4Pairs;
-            grid.x = (unsigned)((passes_max + kL4PassesPerBlock - 1) / kL4PassesPerBlock);
-            static bool attr_set = false;
-            if (!attr_set) {
-                e = cudaFuncSetAttribute(kernels_shared4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set = (e == cudaSuccess);
-            }
-            if (e != cudaSuccess) return e;
-            {
-                dim3 gp((unsigned)((tri_max + 127) / 128), (unsigned)b.n_points);
-                pair_closed_forms_kernel<<<gp, 128, 0, st>>>(b, Kws);
-                lc.launches++;
-                if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            }
-            kernels_shared4_kernel<<<grid, kL4Threads, smem, st>>>(b, Kws, t, p);
-#else
-            const size_t smem = smem_tables + sizeof(double) * (size_t)kTT * kSharedThreads;
-            static bool attr_set = false;
-            if (!attr_set) {
-                e = cudaFuncSetAttribute(kernels_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set = (e == cudaSuccess);
-            }
-            if (e != cudaSuccess) return e;
-            kernels_shared_kernel<<<grid, kSharedThreads, smem, st>>>(b, Kws, t, p);
-#endif
-            lc.launches++;
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            if (lc.split) lc.split_valid = cudaEventRecord(lc.split, st) == cudaSuccess;
-            dim3 gw((unsigned)((tri_max + 127) / 128), (unsigned)b.n_points);
-            switch (p.quad_order) {
-                case 16: kernels_wien_kernel<16><<<gw, 128, 0, st>>>(b, Kws, p); break;
-                case 32: kernels_wien_kernel<32><<<gw, 128, 0, st>>>(b, Kws, p); break;
-                case 96: kernels_wien_kernel<96><<<gw, 128, 0, st>>>(b, Kws, p); break;
-                default: kernels_wien_kernel<64><<<gw, 128, 0, st>>>(b, Kws, p); break;
-            }
-            if (e != cudaSuccess) return e;
-            lc.launches++;
-            return cudaGetLastError();
-        }
         switch (p.quad_order) {
-            case 16: kernels_kernel<16, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;
-            case 32: kernels_kernel<32, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;
             case 96: kernels_kernel<96, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;
             default: kernels_kernel<64, true><<<g, 128, 0, st>>>(b, Kws, t, p); break;
         }
     }
     lc.launches++;
     return cudaGetLastError();
+#else
+    return cudaErrorNotSupported;   // cross-check modes exist only in the test build (-DACRO_CROSSCHECK)
+#endif
 }
 
 cudaError_t launch_count_work(const acro_batch_t& b, const acro_params_t& p, unsigned long long* out, cudaStream_t st,

@@ -1,0 +1,488 @@
+// acro_tmma.cuh -- the production kernel builder: temperature-shared evaluation of the three thermal kernel integrals with the
+// temperature accumulation on the FP64 tensor-core path (DMMA, mma.sync m8n8k4 f64).
+//
+// Same integrals, same panel grid, same limits, same Bose table and partial-panel machinery as the other two forms of the
+// shared kernel (acro_tshared.cuh: one thread per pair; acro_tshared4.cuh: four lanes per pair, FMAs) -- what changes is who
+// does the sum over grid nodes.  For one model point
+//
+//        I[pair][T] = sum_node  W[pair][node] * B[node][T]
+//
+// with W = weight x f(E,E',x_node) (zero outside the pair's range; Legendre-folded weights in the panels cut by a limit) and
+// B = the Bose table of the temperature tile in shared memory: a dense FP64 contraction of shape (pairs x 12) x (12 x 40) per
+// panel.  On B200 DMMA and DFMA share one pipe (tools/microbench/fp64_pipes.cu: 37.0 vs 34.1 TFLOP/s alone, 33-34 mixed), so
+// the tensor path adds no flops -- but one DMMA.8x8x4 replaces 8 DFMA issue slots and, with the fragment layout below, the
+// five 16-byte Bose loads + one weight load per ten FMAs of the four-lane form become one 8-byte load per DMMA; the weights
+// never pass through shared memory at all:
+//
+//   lane = 4 g + q  (g = 0..7, q = 0..3) owns the pairs 2g and 2g+1 of the warp's current 16 pairs (two M-tiles of 8 pairs)
+//   A fragment (8 pairs x 4 nodes):  lane holds W[pair g][node q + 4 ks]  -> the lane EVALUATES nodes q, q+4, q+8 of a panel
+//                                    for its two pairs and the values are the A fragments of the three k-steps as they are;
+//   B fragment (4 nodes x 8 T):      lane loads B[node q + 4 ks][T = 8 nt + g] from the shared-memory table (shared by both
+//                                    M-tiles);
+//   C fragment (8 pairs x 8 T):      lane accumulates I[pair g][T = 8 nt + 2q + {0,1}]: 5 N-tiles x 2 M-tiles = 20 doubles.
+//
+// Stores: the lane's two pairs are neighbours in the packed triangle, so every result leaves as a 16-byte store and the 8
+// lanes of one q write 128 contiguous bytes per temperature (the K planes are padded so that every system starts on a
+// 32-byte boundary: sector-aligned, no partial-sector read-modify-write in DRAM).
+#pragma once
+#include "acro_tshared.cuh"
+
+namespace acro {
+
+#ifndef ACRO_MM_THREADS
+#define ACRO_MM_THREADS 512
+#endif
+constexpr int kMmThreads = ACRO_MM_THREADS;
+constexpr int kMmWarps = kMmThreads / 32;
+constexpr int kMmPairs = kMmWarps * 32;       // pairs per macro-pass of a block (32 per warp: phase A has lane = pair)
+#ifndef ACRO_MM_PASSES
+#define ACRO_MM_PASSES 2                      // macro-passes per block and Bose-table fill
+#endif
+constexpr int kMmPassesPerBlock = ACRO_MM_PASSES;
+#ifndef ACRO_MM_MTILES
+#define ACRO_MM_MTILES 1                      // M-tiles (8 pairs each) a warp carries through the panel walk: 1 or 2
+#endif
+constexpr int kMmM = ACRO_MM_MTILES;
+static_assert(kMmM == 1 || kMmM == 2, "one or two M-tiles per warp");
+constexpr int kMmNT = kTT / 8;                // N-tiles (8 temperatures each)
+constexpr int kMmKS = kPanN / 4;              // k-steps (4 nodes each)
+static_assert(kTT % 8 == 0 && kPanN % 4 == 0, "tile and panel must split into DMMA 8x8x4 shapes");
+
+enum { MM_E = 0, MM_EP, MM_XA9, MM_XB9, MM_XA10, MM_XB10, MM_XA11, MM_XB11, MM_LA9, MM_LB9, MM_LA10, MM_LB10, MM_LA11, MM_LB11,
+       MM_CG, MM_CE, MM_BH, MM_PP, MM_C9, MM_C10, MM_I2EP, MM_FLAGS, MM_NCONST };   // MM_FLAGS: t_on[3] (8 bits each) | active << 24
+
+#ifndef ACRO_MM_ASM_VOLATILE
+#define ACRO_MM_ASM_VOLATILE 1
+#endif
+#if ACRO_MM_ASM_VOLATILE
+#define ACRO_MM_ASM asm volatile
+#else
+#define ACRO_MM_ASM asm
+#endif
+#ifndef ACRO_MM_SWIZZLE
+#define ACRO_MM_SWIZZLE 1                     // Bose-table columns rotated by 4 within their 8-group for nodes 2, 3 (mod 4)
+#endif
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    ACRO_MM_ASM("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// integrand without the Bose factor at a grid node (x, 1/x, y = log x); see integrand_core (acro_fastquad.cuh)
+__device__ __forceinline__ double node_core(int kind, const PairConst& c, double x, double ix, double y, double x_a, double lna) {
+    if (kind == KIND_IC_PHOTON) {
+        const double q = x_a * ix;
+        const double omq = 1.0 - q;
+        return fma(2.0 * q, lna - y, fma(fma(2.0, q, 1.0), omq, c.c9 * omq));
+    } else if (kind == KIND_IC_ELECTRON) {
+        return integrand_core<KIND_IC_ELECTRON>(c, x, x_a, 0.0, false);
+    } else {   // the table holds x^2/(e^{x/T}-1); the pair-creation integrand carries x^1
+        return integrand_core<KIND_PC_ELECTRON>(c, x, x_a, 0.0, false) * ix;
+    }
+}
+
+// this lane's share (nodes q, q+4, q+8 of the sub-interval rule) of the Legendre moments of f over [lo_y, hi_y]
+__device__ __forceinline__ void add_moments_q(int kind, const PairConst& c, double x_a, double lna, double lo_y, double hi_y,
+                                              double p_lo, double h, int q, double mu[kPanN]) {
+    const double hp = 0.5 * (hi_y - lo_y), mp = 0.5 * (hi_y + lo_y);
+    const double ic = 2.0 / h, mid = p_lo + 0.5 * h;
+#pragma unroll 1
+    for (int ss = 0; ss < kMmKS; ++ss) {
+        const int s = q + 4 * ss;
+        const double y = fma(hp, c_glx[gl_offset(kPanN) + s], mp);
+        const double x = fexp(y);
+        double f = node_core(kind, c, x, frcp(x), y, x_a, lna);
+        f *= c_glw[gl_offset(kPanN) + s] * hp;
+        const double tt = (y - mid) * ic;
+        double pm = 1.0, pc = tt;
+        mu[0] += f;
+        mu[1] = fma(f, tt, mu[1]);
+#pragma unroll
+        for (int j = 1; j < kPanN - 1; ++j) {
+            const double pnx = fma(c_leg_rec[j][0] * tt, pc, -c_leg_rec[j][1] * pm);
+            pm = pc; pc = pnx;
+            mu[j + 1] = fma(f, pc, mu[j + 1]);
+        }
+    }
+}
+
+// Partial panel of one pair, executed by its four lanes together (all lanes of the warp call it; `on` marks the pairs that
+// really have a partial panel here).  Returns this lane's three node weights (nodes q, q+4, q+8): the A fragments.
+__device__ __forceinline__ void partial_panel_q(int kind, const PairConst& c, double x_a, double lna, double lo_y, double hi_y,
+                                                double p_lo, double h, double y_layer, int q, bool on,
+                                                const double* __restrict__ s_modal, double w[kMmKS]) {
+    double mu[kPanN];
+#pragma unroll
+    for (int j = 0; j < kPanN; ++j) mu[j] = 0.0;
+    double from = lo_y;
+#pragma unroll 1
+    for (int piece = 0; piece < 3; ++piece) {           // graded cuts at y_layer - 1/4 and y_layer - 1/16, then the rest
+        const double cut = piece == 0 ? y_layer - 0.25 : (piece == 1 ? y_layer - 0.0625 : hi_y);
+        const bool take = on && (piece == 2 || (cut > from && cut < hi_y));
+        if (take) { add_moments_q(kind, c, x_a, lna, from, cut, p_lo, h, q, mu); from = cut; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kPanN; ++j) {
+        mu[j] += __shfl_xor_sync(0xffffffffu, mu[j], 1);
+        mu[j] += __shfl_xor_sync(0xffffffffu, mu[j], 2);
+    }
+#pragma unroll
+    for (int mm = 0; mm < kMmKS; ++mm) {
+        const int m = q + 4 * mm;
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < kPanN; ++j) v = fma(s_modal[j * kPanN + m], mu[j], v);
+        w[mm] = on ? v : 0.0;
+    }
+}
+
+// Pair-only closed forms (Compton shapes per unit electron density, Bethe-Heitler dsigma/dE for Z^2 = 1; cascade.py:383-402,
+// 550-558, 621-639) of every (E,E') pair of every point, thread per (point, pair), into the workspace's closed-form block
+// closed[c * n_pairs_points + pt_pair_off[pt] + loc]: ~1000 instructions that neither kernels_mma_kernel (instruction cache)
+// nor kernels_wien_kernel should carry in their loops.
+__global__ void __launch_bounds__(128) pair_closed_forms_kernel(acro_batch_t b, double* __restrict__ closed) {
+    const int pt = blockIdx.y;
+    const int ne = b.pt_ne[pt];
+    const int64_t tri = (int64_t)ne * (ne + 1) / 2;
+    const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc >= tri) return;
+    const double tn = 2.0 * ne + 1.0;
+    int i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+    i = max(0, min(i, ne - 1));
+    while (i > 0 && tri_row_off(i, ne) > loc) --i;
+    while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
+    const int j = i + (int)(loc - tri_row_off(i, ne));
+    const double* eg = b.e_grid + b.pt_e_off[pt];
+    const double E = eg[i], Ep = eg[j];
+    const int64_t o = b.pt_pair_off[pt] + loc, npp = b.n_pairs_points;
+    closed[o] = kernel_compton_core(E, Ep, 1.0);
+    closed[npp + o] = kernel_compton_core(Ep + kMe - E, Ep, 1.0);
+    closed[2 * npp + o] = !(Ep < E + kMe) ? bh_dsdE_Z2(E, Ep) : 0.0;        // the condition of pair_limits(): xa9 > 0
+}
+
+__global__ void __launch_bounds__(kMmThreads, 1) kernels_mma_kernel(acro_batch_t b, double* __restrict__ Kws,
+                                                                    const double* __restrict__ closed, DeviceTables tb,
+                                                                    acro_params_t p) {
+    extern __shared__ double sm[];
+    const int pt = blockIdx.y;
+    const int ne = b.pt_ne[pt], nt = b.pt_nt[pt], s0 = b.pt_sys_off[pt];
+    const int64_t tri = (int64_t)ne * (ne + 1) / 2;
+    const int passes = (int)((tri + kMmPairs - 1) / kMmPairs);
+    const int pass0 = blockIdx.x * kMmPassesPerBlock, pass_end = min(passes, pass0 + kMmPassesPerBlock);
+    if (pass0 >= passes) return;
+    const double* eg = b.e_grid + b.pt_e_off[pt];
+    const double Tmin = b.sys_T[s0], Tmax = b.sys_T[s0 + nt - 1];
+    const SharedGrid g = shared_grid(Tmin, Tmax, eg[ne - 1], p.Ephb_T_max);
+    const int nn = g.n_pan * kPanN;
+    double* sx = sm;
+    double* six = sx + kMaxPan * kPanN;
+    double* sy = six + kMaxPan * kPanN;
+    double* sB = sy + kMaxPan * kPanN;                 // [nn][kTT]
+    double* sT = sB + (size_t)kMaxPan * kPanN * kTT;   // per-temperature scalars of the tile
+    int64_t* sK = reinterpret_cast<int64_t*>(sT + kTileScalars * kTT);
+    double2* s_lt = reinterpret_cast<double2*>(sT + (kTileScalars + 1) * kTT);
+    double* s_modal = reinterpret_cast<double*>(s_lt + kLogTab);          // [kPanN][kPanN] copy of c_leg_modal
+    double* s_c = s_modal + kPanN * kPanN;                                 // [warps][MM_NCONST][32]
+    for (int k = threadIdx.x; k < kLogTab; k += blockDim.x) s_lt[k] = g_logtab[k];
+    for (int k = threadIdx.x; k < kPanN * kPanN; k += blockDim.x) s_modal[k] = c_leg_modal[k / kPanN][k % kPanN];
+    for (int k = threadIdx.x; k < nn; k += blockDim.x) {
+        double lo, h;
+        panel_geom(g, k / kPanN, lo, h);
+        const double y = lo + 0.5 * h * (1.0 + c_glx[gl_offset(kPanN) + (k % kPanN)]);
+        const double x = fexp(y);
+        sy[k] = y; sx[k] = x; six[k] = frcp(x);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane & 3, gq = lane >> 2;                 // node / temperature-pair index, pair-row index of the fragments
+    double* cw = s_c + (size_t)warp * MM_NCONST * 32;
+    const double x_bot = exp(g.y_bot);
+    const bool deep = x_bot <= 2e-11 * Tmin;
+    const int64_t np = b.n_pairs_total;
+    const int64_t c_off = b.pt_pair_off[pt], npp = b.n_pairs_points;
+    const double a2 = kAlpha * kAlpha;
+
+    for (int t0 = 0; t0 < nt; t0 += kTT) {
+        __syncthreads();
+        if (threadIdx.x < kTT) {
+            const int t = threadIdx.x;
+            const int s = s0 + min(t0 + t, nt - 1);
+            const double T = b.sys_T[s];
+            const Densities d = densities(T, tb.eta, tb.Yp, tb.YHe4);
+            const double T3 = T * T * T;
+            sT[t] = T; sT[kTT + t] = d.ne; sT[2 * kTT + t] = d.nNZ2; sT[3 * kTT + t] = T3 * T3;
+            sT[4 * kTT + t] = p.Ephb_T_max * T;
+            sT[5 * kTT + t] = p.wien_from * T;
+            sT[6 * kTT + t] = kMe2 / (50.0 * T);
+            sT[7 * kTT + t] = -T / kMe2;
+            sK[t] = b.sys_k_off[s];
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nn * kTT; idx += blockDim.x) {
+            const int k = idx / kTT, t = idx % kTT;
+            double v = 0.0;
+            if (t0 + t < nt) {
+                const double T = sT[t];
+                const double x = sx[k];
+                if (x <= sT[4 * kTT + t]) v = x * x * bose_inv(x / T) * (1.0 / kPi2);
+            }
+            // B-fragment loads of a half-warp touch nodes q = 0..3 (row stride kTT = 40 doubles = 8 mod 16 banks-of-8-bytes)
+            // and temperatures g .. g+3: rows q and q+2 would collide; rotating the columns of rows 2, 3 (mod 4) by 4 within
+            // their group of 8 makes the 16 addresses of a half-warp fall into 16 different 8-byte banks
+            sB[ACRO_MM_SWIZZLE ? k * kTT + ((t & ~7) | ((t + ((k & 2) << 1)) & 7)) : idx] = v;
+        }
+        __syncthreads();
+        const int ntile = min(kTT, nt - t0);
+        const double xa_max = sT[5 * kTT + ntile - 1];
+        const double pc_min = sT[6 * kTT + ntile - 1];
+        const double* __restrict__ sBq = sB + (ACRO_MM_SWIZZLE ? ((gq + ((q & 2) << 1)) & 7) : gq);   // B fragment: temperature 8 nt + g
+        for (int pass = pass0; pass < pass_end; ++pass) {
+            const int64_t loc0 = (int64_t)pass * kMmPairs + warp * 32;
+            if (loc0 >= tri) continue;              // warp-uniform: nothing left for this warp
+            // ---- phase A: lane = pair: decode, limits, their logs, closed forms, first-served temperatures
+            __syncwarp();
+            {
+                const int64_t loc = loc0 + lane;
+                const bool active = loc < tri;
+                int i = 0, j = 0;
+                if (active) {
+                    const double tn = 2.0 * ne + 1.0;
+                    i = (int)floor(0.5 * (tn - sqrt(tn * tn - 8.0 * (double)loc)));
+                    i = max(0, min(i, ne - 1));
+                    while (i > 0 && tri_row_off(i, ne) > loc) --i;
+                    while (i < ne - 1 && tri_row_off(i + 1, ne) <= loc) ++i;
+                    j = i + (int)(loc - tri_row_off(i, ne));
+                }
+                const double E = eg[i], Ep = eg[j];
+                const PairLimits L = pair_limits(E, Ep);
+                const double r = E / fmax(Ep - E, 1e-300);
+                const double rr = E / Ep, gg_shape = 1.0 - rr + rr * rr;
+                cw[MM_E * 32 + lane] = E; cw[MM_EP * 32 + lane] = Ep;
+                cw[MM_XA9 * 32 + lane] = L.xa9; cw[MM_XB9 * 32 + lane] = L.xb9;
+                cw[MM_XA10 * 32 + lane] = L.xa10; cw[MM_XB10 * 32 + lane] = L.xb10;
+                cw[MM_XA11 * 32 + lane] = L.xa11; cw[MM_XB11 * 32 + lane] = L.xb11;
+                {
+                    const int64_t o = c_off + (active ? loc : 0);
+                    cw[MM_CG * 32 + lane] = closed[o];
+                    cw[MM_CE * 32 + lane] = closed[npp + o];
+                    cw[MM_BH * 32 + lane] = closed[2 * npp + o];
+                }
+                cw[MM_PP * 32 + lane] = 1112.0 / (10125.0 * kPi) * (a2 * a2) / ((kMe2 * kMe2) * (kMe2 * kMe2)) * 8.0 * (kPi2 * kPi2) /
+                                        63.0 * (Ep * Ep) * (gg_shape * gg_shape);
+                cw[MM_C9 * 32 + lane] = r * r / (2.0 + 2.0 * r);
+                cw[MM_C10 * 32 + lane] = 0.25 * kMe2 / Ep;
+                cw[MM_I2EP * 32 + lane] = 0.5 / Ep;
+                int ton[3];
+#pragma unroll 1
+                for (int kind = 0; kind < 3; ++kind) {
+                    const double xa = kind == 0 ? L.xa9 : (kind == 1 ? L.xa10 : L.xa11);
+                    const double xb = kind == 0 ? L.xb9 : (kind == 1 ? L.xb10 : L.xb11);
+                    const bool has = active && (kind == KIND_PC_ELECTRON ? xb > xa : xa > 0.0);
+                    const bool reg = has && (deep || xa >= x_bot);
+                    // logs of the limits for the panel walk (same calls as the other forms of the shared kernel)
+                    cw[(MM_LA9 + 2 * kind) * 32 + lane] = flog(fmax(xa, 1e-300));
+                    cw[(MM_LB9 + 2 * kind) * 32 + lane] = flog(fmax(xb, 1e-300));
+                    // First temperature of the tile that the shared grid serves: the regime predicates (the expressions
+                    // kernels_wien_kernel evaluates on the same numbers) are monotone in T, which ascends with t.
+                    int lo = 0, hi = ntile;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const bool on = fmin(xb, sT[4 * kTT + mid]) > xa && xa <= sT[5 * kTT + mid] &&
+                                        (kind != KIND_PC_ELECTRON || !(Ep < sT[6 * kTT + mid]));
+                        if (on) hi = mid; else lo = mid + 1;
+                    }
+                    const int v = reg ? lo : kTT;
+                    if (kind == 0) ton[0] = v; else if (kind == 1) ton[1] = v; else ton[2] = v;
+                }
+                cw[MM_FLAGS * 32 + lane] = (double)(ton[0] | (ton[1] << 8) | (ton[2] << 16) | ((active ? 1 : 0) << 24));
+            }
+            __syncwarp();
+            // ---- phase B: sub-passes of 8 kMmM pairs; lane (g, q) owns pairs kMmM g ... kMmM g + kMmM - 1 of the sub-pass
+#pragma unroll 1
+            for (int sub = 0; sub < 4 / kMmM; ++sub) {
+                const int pp0 = sub * 8 * kMmM + kMmM * gq;    // slot 0; slot 1 = pp0 + 1
+                const int64_t loc = loc0 + pp0;
+                // both slots lie inside the system's padded triangle (engine: every system's plane block is padded to a
+                // multiple of 4 entries, so an odd last pair has a pad slot beside it; beyond that nothing may be written)
+                const bool st_ok = kMmM == 2 ? loc < ((tri + 3) & ~(int64_t)3) : loc < tri;
+                const int fl0 = (int)cw[MM_FLAGS * 32 + pp0], fl1 = kMmM == 2 ? (int)cw[MM_FLAGS * 32 + pp0 + 1] : 0;
+                const bool active0 = (fl0 >> 24) & 1, active1 = (fl1 >> 24) & 1;
+                double acc[kMmM][kMmNT][2];
+#pragma unroll 1
+                for (int kind = 0; kind < 3; ++kind) {
+                    // ---------------- the integral of this lane's two pairs on the shared grid, all temperatures of the tile
+#pragma unroll
+                    for (int s = 0; s < kMmM; ++s)
+#pragma unroll
+                        for (int n = 0; n < kMmNT; ++n) { acc[s][n][0] = 0.0; acc[s][n][1] = 0.0; }
+                    // walk parameters of the two slots, packed: first | last << 8 | part_lo << 16 | part_hi << 17 (first = 255: none)
+                    int wk0 = 255, wk1 = 255;
+#pragma unroll
+                    for (int s = 0; s < kMmM; ++s) {
+                        const int pp = pp0 + s;
+                        const double xa = cw[(MM_XA9 + 2 * kind) * 32 + pp], xb = cw[(MM_XB9 + 2 * kind) * 32 + pp];
+                        const double Ep = cw[MM_EP * 32 + pp];
+                        const bool active = s == 0 ? active0 : active1;
+                        const bool has = active && (kind == KIND_PC_ELECTRON ? xb > xa : xa > 0.0);
+                        const bool act = has && xb > xa && xa <= xa_max && (kind != KIND_PC_ELECTRON || !(Ep < pc_min));
+                        const double a = cw[(MM_LA9 + 2 * kind) * 32 + pp], bb = cw[(MM_LB9 + 2 * kind) * 32 + pp];
+                        int p_first = 255, p_last = 0, part = 0;
+                        if (act) {
+                            if (a <= g.y_bot) p_first = g.n_pan - 1;
+                            else { p_first = panel_of(g, a); part |= 1; }
+                            if (bb >= g.y_top) p_last = 0;
+                            else { p_last = panel_of(g, bb); part |= 2; }
+                            if (fmin(bb, g.y_top) <= fmax(a, g.y_bot)) p_first = 255;
+                        }
+                        const int wk = p_first | (p_last << 8) | (part << 16);
+                        if (s == 0) wk0 = wk; else wk1 = wk;
+                    }
+                    int p_lo = max((wk0 & 255) == 255 ? -1 : (wk0 & 255), (wk1 & 255) == 255 ? -1 : (wk1 & 255));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) p_lo = max(p_lo, __shfl_xor_sync(0xffffffffu, p_lo, o));
+#pragma unroll 1
+                    for (int pn = p_lo; pn >= 0; --pn) {
+                        double lo, h;
+                        panel_geom(g, pn, lo, h);
+                        const int pf0 = wk0 & 255, pl0 = (wk0 >> 8) & 255, pf1 = wk1 & 255, pl1 = (wk1 >> 8) & 255;
+                        const bool in0 = pf0 != 255 && pn <= pf0 && pn >= pl0;
+                        const bool in1 = pf1 != 255 && pn <= pf1 && pn >= pl1;
+                        if (!__any_sync(0xffffffffu, in0 || in1)) continue;
+                        const bool lo0 = (wk0 >> 16) & 1, hi0 = (wk0 >> 17) & 1, lo1 = (wk1 >> 16) & 1, hi1 = (wk1 >> 17) & 1;
+                        const bool el = kind == KIND_IC_ELECTRON;
+                        const bool part0 = in0 && ((lo0 && pn == pf0) || (hi0 && pn == pl0) || (el && hi0 && pn == pl0 + 1));
+                        const bool part1 = in1 && ((lo1 && pn == pf1) || (hi1 && pn == pl1) || (el && hi1 && pn == pl1 + 1));
+                        const bool any_part = __any_sync(0xffffffffu, part0 || part1);
+                        const bool any_full = __any_sync(0xffffffffu, (in0 && !part0) || (in1 && !part1));
+                        const int base = pn * kPanN;
+                        double wA[kMmKS], wB[kMmKS];          // A fragments of slot 0 / slot 1 after the loop
+#pragma unroll
+                        for (int mm = 0; mm < kMmKS; ++mm) { wA[mm] = 0.0; wB[mm] = 0.0; }
+#pragma unroll 1
+                        for (int s = 0; s < kMmM; ++s) {
+#pragma unroll
+                            for (int mm = 0; mm < kMmKS; ++mm) wA[mm] = wB[mm];       // rotate: slot 0 ends up in wA (kMmM = 2)
+                            const int pp = pp0 + s;
+                            const bool in = s ? in1 : in0, part = s ? part1 : part0, full = in && !part;
+                            PairConst c;
+                            c.E = cw[MM_E * 32 + pp]; c.Ep = cw[MM_EP * 32 + pp]; c.dE = c.Ep - c.E;
+                            c.c9 = cw[MM_C9 * 32 + pp]; c.c10 = cw[MM_C10 * 32 + pp]; c.i2Ep = cw[MM_I2EP * 32 + pp];
+#if ACRO_FQ_LOGTAB
+                            c.lt = s_lt;
+#endif
+                            const double xa = cw[(MM_XA9 + 2 * kind) * 32 + pp];
+                            const double lna = cw[(MM_LA9 + 2 * kind) * 32 + pp];
+                            double w[kMmKS];
+#pragma unroll
+                            for (int mm = 0; mm < kMmKS; ++mm) w[mm] = 0.0;
+                            if (any_part) {
+                                const int wk = s ? wk1 : wk0;
+                                const bool p_lo_s = (wk >> 16) & 1, p_hi_s = (wk >> 17) & 1;
+                                const int pf_s = wk & 255, pl_s = (wk >> 8) & 255;
+                                const double a_s = fmax(lna, g.y_bot), b_s = fmin(cw[(MM_LB9 + 2 * kind) * 32 + pp], g.y_top);
+                                const bool layer = el && p_hi_s;
+                                const double lo_y = (p_lo_s && pn == pf_s) ? a_s : lo;
+                                const double hi_y = (p_hi_s && pn == pl_s) ? b_s : lo + h;
+                                partial_panel_q(kind, c, xa, lna, part ? lo_y : lo, part ? hi_y : lo + h, lo, h,
+                                                layer ? b_s : hi_y + 2.0, q, part, s_modal, w);
+                            }
+                            if (any_full) {
+                                const double wscale = 0.5 * h;
+#pragma unroll
+                                for (int mm = 0; mm < kMmKS; ++mm) {
+                                    const int m = q + 4 * mm;
+                                    const int k = base + m;
+                                    const double fv = node_core(kind, c, sx[k], six[k], sy[k], xa, lna) * (c_glw[gl_offset(kPanN) + m] * wscale);
+                                    if (full) w[mm] = fv;
+                                }
+                            }
+#pragma unroll
+                            for (int mm = 0; mm < kMmKS; ++mm) wB[mm] = w[mm];
+                        }
+                        // ---- the contraction over the panel's 12 nodes: 3 k-steps x 5 N-tiles x 2 M-tiles of DMMA.8x8x4
+#pragma unroll
+                        for (int ks = 0; ks < kMmKS; ++ks) {
+                            const double* __restrict__ Bk = sBq + (size_t)(base + q + 4 * ks) * kTT;
+#pragma unroll
+                            for (int n = 0; n < kMmNT; ++n) {
+                                const double bf = Bk[8 * n];
+                                if (kMmM == 2) {
+                                    dmma884(acc[0][n][0], acc[0][n][1], wA[ks], bf);
+                                    dmma884(acc[kMmM - 1][n][0], acc[kMmM - 1][n][1], wB[ks], bf);
+                                } else {
+                                    dmma884(acc[0][n][0], acc[0][n][1], wB[ks], bf);
+                                }
+                            }
+                        }
+                    }
+                    // ---------------- epilogue: this lane holds I[pair 2g+s][t = 8 n + 2 q + e]
+                    const int ton0 = (fl0 >> (8 * kind)) & 255, ton1 = (fl1 >> (8 * kind)) & 255;
+                    const int pp1 = pp0 + kMmM - 1;             // slot 1 (= slot 0 for kMmM = 1)
+                    const double Ep0 = cw[MM_EP * 32 + pp0], Ep1 = cw[MM_EP * 32 + pp1];
+                    if (kind != KIND_PC_ELECTRON) {
+                        // ---- e -> gamma (plane 1), e -> e (plane 4)
+                        const double pre0 = 2.0 * kPi * a2 / (Ep0 * Ep0), pre1 = 2.0 * kPi * a2 / (Ep1 * Ep1);
+                        double* __restrict__ out = Kws + (kind == 0 ? 1 : 4) * np + loc;
+#pragma unroll
+                        for (int n = 0; n < kMmNT; ++n)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int t = 8 * n + 2 * q + e;
+                                if (st_ok && t < ntile) {
+                                    double2 v;
+                                    v.x = (active0 && t >= ton0) ? pre0 * acc[0][n][e] : 0.0;
+                                    v.y = (active1 && t >= ton1) ? pre1 * acc[kMmM - 1][n][e] : 0.0;
+                                    if (kMmM == 2) *reinterpret_cast<double2*>(out + sK[t]) = v;
+                                    else out[sK[t]] = v.x;
+                                }
+                            }
+                    } else {
+                        // ---- gamma -> e-/e+ (planes 2, 3) and gamma -> gamma (plane 0)
+                        const double pre0 = 0.25 * kPi * a2 * kMe2 / (Ep0 * Ep0 * Ep0), pre1 = 0.25 * kPi * a2 * kMe2 / (Ep1 * Ep1 * Ep1);
+                        const double bh0 = cw[MM_BH * 32 + pp0], bh1 = cw[MM_BH * 32 + pp1];
+                        const double ce0 = cw[MM_CE * 32 + pp0], ce1 = cw[MM_CE * 32 + pp1];
+                        double* __restrict__ out = Kws + loc;
+#pragma unroll
+                        for (int n = 0; n < kMmNT; ++n)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int t = 8 * n + 2 * q + e;
+                                if (st_ok && t < ntile) {
+                                    const double nz = sT[2 * kTT + t], dne = sT[kTT + t];
+                                    double2 pr, pm;
+                                    pr.x = fma(nz, bh0, (active0 && t >= ton0) ? pre0 * acc[0][n][e] : 0.0);
+                                    pr.y = fma(nz, bh1, (active1 && t >= ton1) ? pre1 * acc[kMmM - 1][n][e] : 0.0);
+                                    pm.x = fma(dne, ce0, pr.x);
+                                    pm.y = fma(dne, ce1, pr.y);
+                                    const int64_t o = sK[t];
+                                    if (kMmM == 2) {
+                                        *reinterpret_cast<double2*>(out + 3 * np + o) = pr;
+                                        *reinterpret_cast<double2*>(out + 2 * np + o) = pm;
+                                    } else {
+                                        out[3 * np + o] = pr.x;
+                                        out[2 * np + o] = pm.x;
+                                    }
+                                }
+                            }
+                        // plane 0 needs no accumulator: a rolled loop (one copy of exp instead of ten)
+                        const double pp_0 = cw[MM_PP * 32 + pp0], pp_1 = cw[MM_PP * 32 + pp1];
+                        const double cg0 = cw[MM_CG * 32 + pp0], cg1 = cw[MM_CG * 32 + pp1];
+#pragma unroll 1
+                        for (int ne2 = 0; ne2 < 2 * kMmNT; ++ne2) {
+                            const int t = 8 * (ne2 >> 1) + 2 * q + (ne2 & 1);
+                            if (st_ok && t < ntile) {
+                                const double mt = sT[7 * kTT + t], T6 = sT[3 * kTT + t], dne = sT[kTT + t];
+                                const double arg0 = Ep0 * mt, arg1 = Ep1 * mt;
+                                double2 v;
+                                v.x = fma(pp_0 * T6, arg0 > -700.0 ? fexp(arg0) : 0.0, dne * cg0);
+                                v.y = fma(pp_1 * T6, arg1 > -700.0 ? fexp(arg1) : 0.0, dne * cg1);
+                                if (kMmM == 2) *reinterpret_cast<double2*>(out + sK[t]) = v;
+                                else out[sK[t]] = v.x;
+                            }
+                        }
+                    }
+                }
+            }
+        }   // passes
+    }
+}
+
+}  // namespace acro

@@ -104,20 +104,23 @@ class Engine(object):
     _cache = {}
 
     @classmethod
-    def get(cls, ii, device=None):
+    def get(cls, ii, device=None, variant="product"):
+        """The engine of (device, input tables).  ``variant="xcheck"`` binds the test build of the library, which also has
+        the per-(E,E',T) cross-check kernel modes (params.kernel_mode = PLAIN_GL / PER_T)."""
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
-        key = (device.index, id(ii), flags.usedb)
+        key = (device.index, id(ii), flags.usedb, variant)
         eng = cls._cache.get(key)
         if eng is None:
-            eng = cls._cache[key] = cls(ii, device)
+            eng = cls._cache[key] = cls(ii, device, variant)
         return eng
 
-    def __init__(self, ii, device):
+    def __init__(self, ii, device, variant="product"):
         if not torch.cuda.is_available():
             raise RuntimeError("acropolis_b200: no CUDA device visible; the hot path has no CPU fallback")
-        self.lib = _lib.load()
+        self.lib = _lib.load(variant)
+        self.variant = variant
         self.ii = ii
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
@@ -129,7 +132,10 @@ class Engine(object):
         Y0 = np.ascontiguousarray(ii.bbn_abundances(), dtype=np.float64)
         if Y0.shape[1] < 3:   # fewer than 3 abundance columns: pad with the mean column
             Y0 = np.ascontiguousarray(np.column_stack([Y0] + [Y0[:, :1]] * (3 - Y0.shape[1])))
-        self.ncol = min(ii.bbn_abundances().shape[1], 3)
+        if ii.bbn_abundances().shape[1] > 3:
+            raise NotImplementedError("acropolis_b200: abundance files with more than 3 columns (mean, high, low) are not "
+                                      "supported by the device path (include/acropolis_b200.h: Y0 is float64[9,3])")
+        self.ncol = ii.bbn_abundances().shape[1]
         t = _lib.Tables()
         t.ratedb = rdb.ctypes.data
         t.ratedb_nT, t.ratedb_nE = params.Tnum, params.Enum
@@ -137,8 +143,9 @@ class Engine(object):
         t.ratedb_Tlog_min, t.ratedb_Tlog_max = params.Tmin_log, params.Tmax_log
         t.cosmo_log10_T, t.cosmo_log10_abs_dTdt, t.n_cosmo = lT.ctypes.data, ldT.ctypes.data, lT.shape[0]
         t.eta = float(ii.parameter("eta"))
-        t.Y0 = Y0[:, :3].copy().ctypes.data
-        self._keep = (rdb, lT, ldT, Y0)
+        Y0c = np.ascontiguousarray(Y0[:, :3])      # must outlive acro_create: the struct holds its address
+        t.Y0 = Y0c.ctypes.data
+        self._keep = (rdb, lT, ldT, Y0, Y0c)
         h = C.c_void_p()
         rc = self.lib.acro_create(C.byref(h), device.index, C.byref(t), None)
         if rc != 0:
@@ -163,9 +170,10 @@ class Engine(object):
 
     def _sync_params(self):
         key = (params.quad_order, params.pdi_cell_order, params.Emin, params.approx_zero, params.Ephb_T_max,
-               params.E_EC_max, bool(flags.usedb and self._use_db), int(params.kernel_mode), float(params.wien_from))
+               params.E_EC_max, bool(flags.usedb and self._use_db), int(params.kernel_mode), float(params.wien_from),
+               bool(flags.universal))
         if key != self._params_key:
-            p = _lib.Params(*key[:6], int(key[6]), key[7], key[8])
+            p = _lib.Params(*key[:6], int(key[6]), key[7], key[8], int(key[9]), 0)
             self._check(self.lib.acro_set_params(self.h, C.byref(p)), "acro_set_params")
             self._params_key = key
 
@@ -193,9 +201,15 @@ class Engine(object):
         S = int(sys_point.shape[0])
         sys_f_off = np.zeros(S, dtype=np.int64)
         np.cumsum(sys_ne[:-1], out=sys_f_off[1:])
+        # every system's packed triangle is padded to a multiple of 4 entries (32 bytes): the builder's 16-byte stores of
+        # neighbouring pairs stay aligned and every 64-byte run it writes covers whole DRAM sectors
         sys_k_off = np.zeros(S, dtype=np.int64)
-        tri = sys_ne * (sys_ne + 1) // 2
+        tri = (sys_ne * (sys_ne + 1) // 2 + 3) & ~np.int64(3)
         np.cumsum(tri[:-1], out=sys_k_off[1:])
+        ne64 = ne.astype(np.int64)
+        tri_pt = (ne64 * (ne64 + 1) // 2 + 3) & ~np.int64(3)
+        pt_pair_off = np.zeros(P, dtype=np.int64)
+        np.cumsum(tri_pt[:-1], out=pt_pair_off[1:])
         modes = {p.sc_mode for p in points}
         if modes == {_lib.SC_NONE}:
             sc_mode, sc, sc_E = _lib.SC_NONE, np.zeros(0), np.zeros(0)
@@ -214,7 +228,7 @@ class Engine(object):
                 else:
                     parts.append(np.zeros(len(p.T) * 3 * len(p.E_grid)))
             sc = np.concatenate(parts)
-        a = dict(pt_ne=ne, pt_nt=nt, pt_e_off=pt_e_off, pt_sys_off=pt_sys_off,
+        a = dict(pt_ne=ne, pt_nt=nt, pt_e_off=pt_e_off, pt_sys_off=pt_sys_off, pt_pair_off=pt_pair_off,
                  pt_e0=np.fromiter((p.E0 for p in points), dtype=np.float64, count=P),
                  pt_t_at_tmax=np.fromiter((p.t_at_tmax for p in points), dtype=np.float64, count=P),
                  e_grid=np.concatenate([p.E_grid for p in points]),
@@ -223,16 +237,19 @@ class Engine(object):
                  s0=np.concatenate([p.S0 for p in points]).reshape(-1),
                  sc=np.ascontiguousarray(sc, dtype=np.float64), sc_E=np.ascontiguousarray(sc_E, dtype=np.float64))
         counts = dict(n_points=P, n_systems=S, n_energy_total=int(ne.sum()), n_sys_energy_total=int(sys_ne.sum()),
-                      n_pairs_total=int(tri.sum()), ne_max=int(ne.max()), nt_max=int(nt.max()), sc_mode=sc_mode)
+                      n_pairs_total=int(tri.sum()), n_pairs_points=int(tri_pt.sum()), ne_max=int(ne.max()), nt_max=int(nt.max()),
+                      sc_mode=sc_mode)
         return a, counts
 
-    _ORDER = ("pt_ne", "pt_nt", "pt_e_off", "pt_sys_off", "pt_e0", "pt_t_at_tmax", "e_grid", "sys_point", "sys_T",
+    _ORDER = ("pt_ne", "pt_nt", "pt_e_off", "pt_sys_off", "pt_pair_off", "pt_e0", "pt_t_at_tmax", "e_grid", "sys_point", "sys_T",
               "sys_f_off", "sys_k_off", "s0", "sc", "sc_E")
 
     @staticmethod
     def point_cost_bytes(ne, nt):
-        """Workspace bytes one point needs (5 K planes + rate work list + cross-section table of the pdi cells)."""
-        return nt * (5 * 8 * (ne * (ne + 1) // 2) + 32 * ne) + 4 * nt + 512 + 16 * 17 * 8 * ne
+        """Workspace bytes one point needs (5 K planes + pair closed forms + rate work list + cross-section table of the
+        pdi cells)."""
+        tri = (ne * (ne + 1) // 2 + 3) & ~3
+        return nt * (5 * 8 * tri + 32 * ne) + 24 * tri + 4 * nt + 512 + 16 * 17 * 8 * ne
 
     MAX_POINTS_PER_CHUNK = 32768     # the kernels index points with blockIdx.y (limit 65535)
 
@@ -370,10 +387,19 @@ class Engine(object):
         return np.array(list(ms), dtype=np.float64)
 
     def kernel_split_ms(self):
-        """(temperature-shared kernel, Wien-tail kernel) device time [ms] of the last launch."""
-        ms = (C.c_float * 2)()
+        """Device time [ms] of the kernel builder's launches in the last acro_run_batch, in the order of
+        ``kernel_split_names()``."""
+        ms = (C.c_float * 3)()
         self._check(self.lib.acro_last_kernel_split_ms(self.h, C.byref(ms)), "acro_last_kernel_split_ms")
         return np.array(list(ms), dtype=np.float64)
+
+    @staticmethod
+    def kernel_split_names():
+        return _lib.KERNEL_SPLIT_NAMES
+
+    @staticmethod
+    def n_kernel_splits():
+        return len(_lib.KERNEL_SPLIT_NAMES)
 
     def _arena_for_chunk(self):
         # two arenas alternate so that chunk n+1 can be staged while chunk n is still being read by the GPU

@@ -2,7 +2,7 @@
 usedb = True       # interpolate the two tabulated rates from rates.db (device resident)
 verbose = True
 debug = False
-universal = False  # universal-spectrum shortcut (cascade.py:774-812): not on the CUDA path
+universal = False  # universal photon spectrum instead of the cascade solution (cascade.py:774-812, nucl.py:416-422)
 
 
 def set_universal(value):

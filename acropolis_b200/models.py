@@ -147,6 +147,9 @@ class AbstractModel(ABC):
         eng = self._engine()
         if self._sMatpBuffer is None:
             out = eng.run([self.point_spec()], want=("mpdi", "mdcy", "status"))
+            if int(out["status"][0]) & _lib.ST_NONFINITE:    # range warnings were printed by _warn_ranges()
+                print_warning("Non-finite abundances for this parameter point.",
+                              "acropolis_b200.models.AbstractModel._pdi_matrix")
             self._sMatpBuffer = (out["mpdi"][0], out["mdcy"][0])
         mpdi, mdcy = self._sMatpBuffer
         if _neutron_foldable(self, mpdi, mdcy):

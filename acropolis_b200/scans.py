@@ -103,6 +103,39 @@ def gather_rows(local_idx, local_rows, n_total, width, dist=None):
     return full
 
 
+_CHAIN_HOOKS = ("run_disintegration", "_pdi_matrix", "_pred_matrix", "_postd_matrix", "_squeeze_decays")
+
+
+def uses_builtin_chain(model):
+    """True if the model takes the stock route from (mpdi, mdcy) to the abundances (reference models.py:43-165), which the
+    device computes for a whole batch.  A user subclass that overrides one of these hooks is honoured in the reference by
+    ``_run_single`` calling ``model.run_disintegration()`` (scans.py:118); here such a model is run through its own
+    ``run_disintegration()`` too (one engine call per model -- slow but faithful)."""
+    cls = type(model)
+    return all(getattr(cls, n) is getattr(AbstractModel, n) for n in _CHAIN_HOOKS)
+
+
+def report_status(status, where):
+    """Decode the per-point status words of a batch (include/acropolis_b200.h ACRO_ST_*) into the reference's messages:
+    E0 > 1 GeV and an uncovered temperature range are warnings there (models.py:47-61); non-finite abundances have no
+    counterpart in the reference (it would print NaN rows) -- they are reported with their count."""
+    from acropolis_b200 import _lib
+    from acropolis_b200.pprint import print_warning
+    status = np.asarray(status, dtype=np.int64).reshape(-1)
+    if status.size == 0:
+        return 0
+    n_e0 = int(np.count_nonzero(status & _lib.ST_E0_ABOVE_GEV))
+    n_t = int(np.count_nonzero(status & _lib.ST_T_OUTSIDE))
+    n_bad = int(np.count_nonzero(status & _lib.ST_NONFINITE))
+    if n_e0:
+        print_warning("Injection energy > 1 GeV for %d point(s). Results cannot be trusted." % n_e0, where)
+    if n_t:
+        print_warning("Temperature range not covered by input data for %d point(s). Results cannot be trusted." % n_t, where)
+    if n_bad:
+        print_warning("Non-finite abundances for %d point(s)." % n_bad, where)
+    return n_bad
+
+
 def run_models(models, devices=None, want_matp=False):
     """Final abundances of many models at once -> Yf[N, 9, ncol]  (N x ``run_disintegration``, reference
     models.py:43-91).  Trivial models (E0 <= Emin) get the post-decayed input abundances.  With ``want_matp`` the
@@ -115,7 +148,10 @@ def run_models(models, devices=None, want_matp=False):
     matp = [None] * N
     work = []
     for i, m in enumerate(models):
-        if m.is_trivial():
+        if not uses_builtin_chain(m):
+            Yf[i] = m.run_disintegration()      # the model's own hooks decide (reference scans.py:118)
+            matp[i] = m.get_matp_buffer()
+        elif m.is_trivial():
             Yf[i] = m._squeeze_decays(m._sII.bbn_abundances())
         else:
             work.append(i)
@@ -140,6 +176,7 @@ def run_models(models, devices=None, want_matp=False):
                     for d, sh in zip(devices, shards) if len(sh)]
             parts = [(sh, f.result()) for sh, f in zip([s for s in shards if len(s)], futs)]
     for sh, out in parts:
+        report_status(out["status"], "acropolis_b200.scans.run_models")
         for k, j in enumerate(sh):
             Yf[work[j]] = out["Yf"][k][:, :ncol]
             if want_matp:
@@ -188,19 +225,21 @@ def _run_points_pipelined(model, param_sets, devices, group, first_group, growth
     def finish(entry):
         idx, pend = entry
         out = eng.collect(pend, want=("Yf", "status"))
+        statuses.append(out["status"])
         for k, i in enumerate(idx):
             Y = out["Yf"][k][:, :ncol]
             p = param_sets[i]
             rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
 
-    models, ncol = [None] * N, 3
+    models, ncol, statuses = [None] * N, 3, []
 
     def build(i):
         """Model of point i; a point below all thresholds is answered on the spot (a scan may start with hundreds)."""
         nonlocal ncol, eng
         m = models[i] = model(**param_sets[i])
-        if m.is_trivial():
-            Y = m._squeeze_decays(m._sII.bbn_abundances())
+        own = not uses_builtin_chain(m)
+        if own or m.is_trivial():
+            Y = m.run_disintegration() if own else m._squeeze_decays(m._sII.bbn_abundances())
             ncol = Y.shape[1]
             p = param_sets[i]
             rows[i] = [*[p[key] for key in sorted(p)], *Y.transpose().reshape(Y.size)]
@@ -241,6 +280,8 @@ def _run_points_pipelined(model, param_sets, devices, group, first_group, growth
             target = min(group, growth * target)
     for entry in in_flight:
         finish(entry)
+    if statuses:
+        report_status(np.concatenate(statuses), "acropolis_b200.scans.run_points")
     # A model holds lists of its own bound methods (get_source_terms, as in the reference): a reference cycle per point that
     # only the cyclic collector could free.  These models never leave this function, so the cycles are cut here and the
     # thousands of objects of a call are released by reference counting instead of piling up for a later collection.
@@ -292,6 +333,12 @@ class BufferedScanner(object):
     def _row(scanp_set, Yb):
         return [*[scanp_set[key] for key in sorted(scanp_set)], *Yb.transpose().reshape(Yb.size)]
 
+    @staticmethod
+    def _ncol():
+        """Abundance columns of the shared input file (rows are [2 + 9*ncol] wide)."""
+        from acropolis_b200.input import shared_input_interface, locate_sm_file
+        return shared_input_interface(locate_sm_file()).bbn_abundances().shape[1]
+
     def scan_points(self):
         """The flattened list of parameter dicts in the reference's order (scans.py:193-208)."""
         key1, key2 = self._sScanp_id
@@ -323,8 +370,9 @@ class BufferedScanner(object):
         mine = np.arange(N)
         if world > 1:   # cheap cost proxy before any model is built: the E0-dependent grid size is not known here,
             mine = np.arange(rank, N, world)   # so deal points round-robin (neighbouring points cost the same)
-        rows = run_points(lambda **sp: self._build(sp), [pts[i] for i in mine], devices=devices).reshape(len(mine), -1)
-        width = rows.shape[1] if len(mine) else 29
+        width = 2 + 9 * self._ncol()
+        rows = (run_points(lambda **sp: self._build(sp), [pts[i] for i in mine], devices=devices).reshape(len(mine), width)
+                if len(mine) else np.zeros((0, width)))      # a rank without points still enters the gather
         return gather_rows(mine, rows, N, width) if world > 1 else rows
 
     # -- one fast parameter: full computation for the first fast value, rescaled mpdi for the rest (scans.py:127-176)
@@ -340,7 +388,7 @@ class BufferedScanner(object):
         Yl, matp = run_models(lead_models, devices=devices, want_matp=True) if lead_models else (None, [])
         it = iter(matp)
         bufs = [next(it) if f is not None else None for f in lead]
-        ncol = models[0][0]._sII.bbn_abundances().shape[1] if models else 3
+        ncol = self._ncol()
         Yf = np.zeros((len(slow), nf, 9, ncol))
         jobs = []   # (row, f, mpdi, mdcy, factor, t_at_tmax)
         for r, row in enumerate(models):
@@ -348,6 +396,9 @@ class BufferedScanner(object):
                 if bufs[r] is None or f < lead[r] or m.is_trivial():
                     # before the buffer exists the reference runs the model itself: trivial by construction
                     Yf[r, f] = m._squeeze_decays(m._sII.bbn_abundances()) if m.is_trivial() else np.nan
+                elif not uses_builtin_chain(m):      # user hooks between (mpdi, mdcy) and Yf: the model's own chain
+                    m.set_matp_buffer(self._rescale_matp_buffer(bufs[r], fast[f] / fast[lead[r]]))
+                    Yf[r, f] = m.run_disintegration()
                 else:
                     m.set_matp_buffer(self._rescale_matp_buffer(bufs[r], fast[f] / fast[lead[r]]))
                     jobs.append((r, f, bufs[r][0], bufs[r][1], fast[f] / fast[lead[r]], m._t_at_tmax()))
@@ -358,6 +409,6 @@ class BufferedScanner(object):
             for (r, f, *_), y in zip(jobs, Y):
                 Yf[r, f] = y[:, :ncol]
         idx = np.array([s * nf + f for s in slow for f in range(nf)], dtype=np.int64)
-        rows = np.array([self._row(pts[i], Yf[k // nf, k % nf]) for k, i in enumerate(idx)]).reshape(len(idx), -1)
         width = 2 + 9 * ncol
+        rows = np.array([self._row(pts[i], Yf[k // nf, k % nf]) for k, i in enumerate(idx)]).reshape(len(idx), width)
         return gather_rows(idx, rows, len(pts), width) if world > 1 else rows

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ACRO_ABI_VERSION 2
+#define ACRO_ABI_VERSION 3
 
 #define ACRO_NX 3   /* cascade species: photon, electron, positron        (cascade.py:718)        */
 #define ACRO_NY 9   /* nuclides n,p,d,t,He3,He4,Li6,Li7,Be7              (nucl.py:32-42)          */
@@ -56,6 +56,8 @@ extern "C" {
 /* how the three thermal kernel integrals are evaluated (same integrals and limits either way) */
 #define ACRO_KERNELS_FAST      0  /* temperature-shared panel grid (Bose table in shared memory) + Gauss-Laguerre on the Wien
                                      tail + reduced Gauss-Legendre elsewhere (default)                                */
+/* the next two are cross-check modes of the test build (libacropolis_b200_xcheck.so, -DACRO_CROSSCHECK); the product
+ * library rejects them in acro_set_params */
 #define ACRO_KERNELS_PLAIN_GL  1  /* plain Q-point Gauss-Legendre in log(eps_bar) with the reference's F/G incl. range tests */
 #define ACRO_KERNELS_PER_T     2  /* as FAST but every (pair,T) integral evaluated on its own (no temperature sharing)    */
 
@@ -92,6 +94,10 @@ typedef struct {
                               * is evaluated per (E,E',T) with Gauss-Laguerre on the Wien tail, the others on the
                               * temperature-shared grid.  e <= wien_from <= e^2.  Default e^2 = 7.389 (kernel entries
                               * within 1e-7 of the converged integrals); e = 2.718 gives 1e-9 at ~1.4x the time.    */
+    int32_t universal;       /* flags.universal (flags.py:33-41): the photon spectrum is the universal one of
+                              * cascade.py:774-812 instead of the cascade solution, and the pdi integrals stop at
+                              * min(E0, me^2/(22T)) (nucl.py:416-422); the kernel and solve work is skipped.        */
+    int32_t reserved;
 } acro_params_t;
 
 /*
@@ -103,7 +109,9 @@ typedef struct {
     int32_t n_systems;           /* S                                                        */
     int64_t n_energy_total;      /* sum_p NE_p   (length of e_grid)                          */
     int64_t n_sys_energy_total;  /* sum_s NE_s   (rows of G / F / dense SC)                  */
-    int64_t n_pairs_total;       /* sum_s NE_s (NE_s+1)/2   (entries of one K plane)         */
+    int64_t n_pairs_total;       /* sum_s pad4(NE_s (NE_s+1)/2): entries of one K plane; every system's packed triangle is
+                                    padded to a multiple of 4 entries (32-byte sectors), so this is a multiple of 4  */
+    int64_t n_pairs_points;      /* sum_p pad4(NE_p (NE_p+1)/2): entries of one pair-constant block of the workspace */
     int32_t ne_max;              /* max_p NE_p                                               */
     int32_t nt_max;              /* max_p NT_p                                               */
     int32_t sc_mode;             /* ACRO_SC_*                                                */
@@ -113,6 +121,7 @@ typedef struct {
     const int32_t* pt_nt;        /* NT_p  (nucl.py:473)                                      */
     const int64_t* pt_e_off;     /* offset of the point's grid in e_grid                     */
     const int32_t* pt_sys_off;   /* index of the point's first system                        */
+    const int64_t* pt_pair_off;  /* offset of the point's pairs in a pair-constant block: prefix sum of pad4(tri_p) */
     const double*  pt_e0;        /* injection energy E0 (delta-source position)              */
     const double*  pt_t_at_tmax; /* cosmic time [s] at T_max, for the pre-decay matrix (models.py:140-145) */
     /* per energy [n_energy_total] */
@@ -121,7 +130,7 @@ typedef struct {
     const int32_t* sys_point;    /* owning point                                             */
     const double*  sys_T;        /* temperature T_s                                          */
     const int64_t* sys_f_off;    /* row offset of the system in G / F / dense SC             */
-    const int64_t* sys_k_off;    /* entry offset of the system in each K plane               */
+    const int64_t* sys_k_off;    /* entry offset of the system in each K plane: prefix sum of pad4(tri_s), multiple of 4 */
     const double*  s0;           /* [S,3] monochromatic source terms S0_X(T_s) (cascade.py:763) */
     const double*  sc;           /* see ACRO_SC_*; may be NULL for ACRO_SC_NONE              */
     const double*  sc_E;         /* [n_energy_total,3] for ACRO_SC_SEPARABLE, else NULL       */
@@ -188,8 +197,9 @@ int acro_measure_fp64_peak(acro_handle_t* h, double* tflops);
  * ms[0]=rates, ms[1]=kernels, ms[2]=solve+pdi, ms[3]=matrix.  Synchronises on the recorded events.             */
 int acro_last_stage_ms(acro_handle_t* h, float ms[4]);
 
-/* Split of ms[1] for kernel_mode = ACRO_KERNELS_FAST: ms[0] = temperature-shared kernel, ms[1] = Wien-tail kernel. */
-int acro_last_kernel_split_ms(acro_handle_t* h, float ms[2]);
+/* Split of ms[1] for kernel_mode = ACRO_KERNELS_FAST: ms[0] = pair_closed_forms_kernel, ms[1] = kernels_mma_kernel
+ * (temperature-shared grid), ms[2] = kernels_wien_kernel (Wien tail). */
+int acro_last_kernel_split_ms(acro_handle_t* h, float ms[3]);
 
 /* Work census of a (device-resident) batch for the roofline's algorithmic-flop figure: out[0] = (system,i,j>=i) pairs,
  * out[1..3] = pairs with a non-empty range for the e->gamma, e->e and gamma->e thermal integrals (the reference's own

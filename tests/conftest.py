@@ -36,3 +36,15 @@ def gpu_engine():
     from acropolis_b200.input import shared_input_interface
     from acropolis_b200.engine import Engine
     return Engine.get(shared_input_interface())
+
+
+@pytest.fixture(scope="session")
+def xcheck_engine():
+    """Engine bound to the TEST build of the library (-DACRO_CROSSCHECK): the product kernels plus the per-(E,E',T)
+    cross-check modes kernel_mode = PLAIN_GL / PER_T, which the product library rejects."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from acropolis_b200.input import shared_input_interface
+    from acropolis_b200.engine import Engine
+    return Engine.get(shared_input_interface(), variant="xcheck")

@@ -293,14 +293,14 @@ def test_wien_from_parameter(gpu_engine):
             gpu_engine.kernels_of(sp, 0)
     K2, _ = gpu_engine.kernels_of(sp, 19)          # default again (a rejected parameter set leaves the old one active)
     ms = gpu_engine.kernel_split_ms()
-    assert ms.shape == (2,) and (ms > 0).all()
+    assert ms.shape == (3,) and (ms > 0).all() and len(gpu_engine.kernel_split_names()) == 3
     with wien_from(E1):
         K1, _ = gpu_engine.kernels_of(sp, 19)
     assert np.array_equal(K1 != 0, K2 != 0)
     assert relerr(K2, K1) < 1e-7
 
 
-def test_fast_kernels_match_plain_gauss_legendre(gpu_engine):
+def test_fast_kernels_match_plain_gauss_legendre(gpu_engine, xcheck_engine):
     """Production evaluation of the thermal integrals (Gauss-Laguerre on the Wien tail, reduced integrands, Q/2 rule on
     short ranges) against the plain Gauss-Legendre evaluation at Q=96 with the reference's F/G range tests."""
     import acropolis_b200.params as params
@@ -310,7 +310,7 @@ def test_fast_kernels_match_plain_gauss_legendre(gpu_engine):
         for it in its:
             try:
                 params.kernel_mode, params.quad_order = 1, 96
-                Kp, Gp = gpu_engine.kernels_of(sp, it)
+                Kp, Gp = xcheck_engine.kernels_of(sp, it)
             finally:
                 params.kernel_mode, params.quad_order = 0, 64
             Kf, Gf = gpu_engine.kernels_of(sp, it)

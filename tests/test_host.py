@@ -28,11 +28,27 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.acro_abi_version() == 2
+    assert lib.acro_abi_version() == 3 == _lib.ABI_VERSION
     p = _lib.Params()
     lib.acro_default_params(p)
-    assert (p.quad_order, p.pdi_cell_order, p.Emin, p.approx_zero, p.Ephb_T_max, p.E_EC_max, p.use_db, p.kernel_mode) == \
-        (64, 8, 1.5, 1e-200, 200.0, 10.0, 1, 0)
+    assert (p.quad_order, p.pdi_cell_order, p.Emin, p.approx_zero, p.Ephb_T_max, p.E_EC_max, p.use_db, p.kernel_mode, p.universal) == \
+        (64, 8, 1.5, 1e-200, 200.0, 10.0, 1, 0, 0)
+    # the test build (cross-check kernel modes) exports the same ABI
+    x = _lib.load("xcheck")
+    assert x.acro_abi_version() == 3 and all(getattr(x, n) is not None for n in declared)
+
+
+def test_product_library_ships_without_crosscheck_kernels():
+    """The product .so holds the production kernels only; the cross-check instantiations live in the
+    test build."""
+    from acropolis_b200 import _lib
+    def kernels(path):
+        out = subprocess.run(["cuobjdump", "-lelf", path], capture_output=True, text=True).stdout  # noqa: F841
+        sy = subprocess.run(["cuobjdump", "-res-usage", path], capture_output=True, text=True).stdout
+        return sy
+    prod, xc = kernels(_lib.LIB_PATH), kernels(_lib.XCHECK_LIB_PATH)
+    assert "kernels_mma_kernel" in prod and "kernels_wien_kernel" in prod and "acro14kernels_kernelI" not in prod
+    assert "acro14kernels_kernelI" in xc and "kernels_mma_kernel" in xc
 
 
 def test_library_is_built_for_sm_100a():
@@ -168,10 +184,13 @@ def test_assemble_offsets():
     a, c = Engine.assemble(pts)
     assert c["n_points"] == 3 and c["n_systems"] == 10 and c["n_energy_total"] == 60 and c["ne_max"] == 33 and c["nt_max"] == 5
     assert c["n_sys_energy_total"] == 10 * 3 + 17 * 5 + 33 * 2
-    assert c["n_pairs_total"] == 55 * 3 + 153 * 5 + 561 * 2
+    # every system's packed triangle is padded to a multiple of 4 entries: 55 -> 56, 153 -> 156, 561 -> 564
+    assert c["n_pairs_total"] == 56 * 3 + 156 * 5 + 564 * 2 and c["n_pairs_points"] == 56 + 156 + 564
+    assert list(a["pt_pair_off"]) == [0, 56, 56 + 156]
+    assert np.all(a["sys_k_off"] % 4 == 0)
     assert list(a["pt_e_off"]) == [0, 10, 27] and list(a["pt_sys_off"]) == [0, 3, 8]
     assert list(a["sys_point"]) == [0] * 3 + [1] * 5 + [2] * 2
-    assert list(a["sys_f_off"][:5]) == [0, 10, 20, 30, 47] and a["sys_k_off"][3] == 165 and a["sys_k_off"][4] == 165 + 153
+    assert list(a["sys_f_off"][:5]) == [0, 10, 20, 30, 47] and a["sys_k_off"][3] == 168 and a["sys_k_off"][4] == 168 + 156
     assert c["sc_mode"] == 0
 
 
