@@ -45,6 +45,26 @@ class SpectrumGenerator(object):
         sol = self.get_spectra(E0, S0f, SCf, [T])[0]
         return sol[0:2, :] if not allX else sol
 
+    def get_universal_spectrum(self, E0, S0f, SCf, T, offset=0.):
+        """The universal photon spectrum of astro-ph/0211258 (reference cascade.py:774-812) -> float64[2, NE] (rows E,
+        F_photon): SN K0 (EX/E)^{3/2} / Gamma_gamma below EX = me^2/(80T), SN K0 (EX/E)^2 / Gamma_gamma up to (1+offset) EC
+        with EC = me^2/(22T), floored at approx_zero above.  The total photon rates come from the device (closed forms +
+        rates.db interpolation / direct integrals); with ``flags.universal`` the batched path applies the same formula inside
+        solve_pdi_kernel (offset = 5e-2, nucl.py:419-421)."""
+        from math import log
+        E_grid = energy_grid(E0)
+        EC, EX = params.me2 / (22. * T), params.me2 / (80. * T)
+        K0 = E0 / ((EX**2.) * (2. + log(EC / EX)))
+        SN = sum(float(S0X(T)) for S0X in S0f)
+        rate = self._sEngine.total_rates(E_grid, np.full(len(E_grid), T))[:, 0]
+        F = np.zeros(len(E_grid))
+        lo = E_grid < EX
+        mid = (~lo) & (E_grid <= (1. + offset) * EC)
+        F[lo] = SN * K0 * (EX / E_grid[lo])**1.5 / rate[lo]
+        F[mid] = SN * K0 * (EX / E_grid[mid])**2.0 / rate[mid]
+        F[F < params.approx_zero] = params.approx_zero
+        return np.array([E_grid, F])
+
     def get_kernels(self, E0, T):
         """(E_grid, G[3,NE], K[5,NE,NE]) at one temperature; K planes ordered gg, eg, ge-, ge+, ee, i.e. the reference's
         K[X,Xp] for (X,Xp) = (0,0), (0,1)=(0,2), (1,0), (2,0), (1,1)=(2,2) (cascade.py:751-755)."""

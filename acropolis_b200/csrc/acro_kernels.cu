@@ -695,7 +695,10 @@ __global__ void __launch_bounds__(128) pdi_sigma_kernel(acro_batch_t b, double* 
     }
 }
 
-__global__ void __launch_bounds__(128) solve_pdi_kernel(acro_batch_t b, const double* __restrict__ G, double* __restrict__ Fout,
+#ifndef ACRO_SV_MINBLOCKS
+#define ACRO_SV_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_batch_t b, const double* __restrict__ G, double* __restrict__ Fout,
                                                         double* __restrict__ pdi, const double* __restrict__ Kws,
                                                         const double* __restrict__ sig, acro_params_t p, int smem_stride) {
     extern __shared__ double smem[];

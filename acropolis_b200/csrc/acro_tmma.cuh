@@ -84,7 +84,10 @@ __device__ __forceinline__ void add_moments_q(int kind, const PairConst& c, doub
                                               double p_lo, double h, int q, double mu[kPanN]) {
     const double hp = 0.5 * (hi_y - lo_y), mp = 0.5 * (hi_y + lo_y);
     const double ic = 2.0 / h, mid = p_lo + 0.5 * h;
-#pragma unroll 1
+#ifndef ACRO_MM_MOM_UNROLL
+#define ACRO_MM_MOM_UNROLL 1          // sub-interval nodes evaluated together (independent chains) in the partial panels
+#endif
+ACRO_UNROLL(ACRO_MM_MOM_UNROLL)
     for (int ss = 0; ss < kMmKS; ++ss) {
         const int s = q + 4 * ss;
         const double y = fma(hp, c_glx[gl_offset(kPanN) + s], mp);

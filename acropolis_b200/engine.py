@@ -471,7 +471,7 @@ class Engine(object):
         d_T = torch.from_numpy(np.concatenate(T_list).astype(np.float64)).to(dev)
         d_pdi = torch.from_numpy(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, _lib.NR) for p in pdi_list])
                                  .reshape(-1)).to(dev)
-        d_lo = torch.from_numpy(np.asarray(T_lo, dtype=np.float64)).to(dev) if T_lo is not None else None
+        d_lo = torch.from_numpy(np.array(T_lo, dtype=np.float64)).to(dev) if T_lo is not None else None
         d_tt = torch.from_numpy(np.asarray(t_at_tmax if t_at_tmax is not None else np.zeros(P), dtype=np.float64)).to(dev)
         mpdi = torch.empty(P * 81, dtype=torch.float64, device=dev)
         mdcy = torch.empty(P * 81, dtype=torch.float64, device=dev)

@@ -478,6 +478,63 @@ def case_pdi_exact():
     np.savez_compressed(os.path.join(OUT, "pdi_exact.npz"), **out)
 
 
+def case_converged():
+    """'Converged reference' answers for the five tight points: every quadrature downstream of the (tight, eps = 1e-9) cascade
+    spectra redone with the REFERENCE'S OWN integrand functions handed to scipy.integrate.quad with break points at the grid
+    knots and a subdivision limit that is never reached -- pdi rates (nucl.py:428-451: Fph_s, limit 2000), the T-integrals of
+    MatrixGenerator (nucl.py:563-614: _pdi_kernel_ij / _dcy_kernel_ij, limit 20000, break points at the T-grid knots), then
+    expm and the decay matrices as in models.py:84-89.  The reference itself at eps = 1e-9 keeps quad's default limit = 50
+    (pdi) / 100 (T) without break points and stops at 2e-4 / 3e-6 on these kinked integrands (IntegrationWarning); the
+    fixture separates that from the CUDA path's own error."""
+    import numpy as np
+    import warnings
+    from math import log, exp
+    from scipy.integrate import quad
+    from scipy.linalg import expm
+    cascade, nucl = _import_reference()
+    from acropolis.utils import LogInterp
+    from acropolis.input import InputInterface, locate_sm_file
+    ii = InputInterface(locate_sm_file())
+    nr = nucl.NuclearReactor(None, None, (1e-3, 1e-2), 10., ii)
+    out = {}
+    for tag in ("cfg1_decay_tight", "decay_ee_tight", "cfg2_annih_tight", "annih_pwave_tight", "resonance_b3_tight"):
+        fx = np.load(os.path.join(OUT, tag + ".npz"))
+        E0, E_grid, T, F, S0 = float(fx["E0"]), fx["E_grid"], fx["T"], fx["F"], fx["S0"]
+        pdi = np.zeros((len(T), 17))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for it, Ti in enumerate(T):
+                EC = nucl.me2 / (22. * Ti)
+                Emax = min(E0, nucl.E_EC_max * EC)
+                Fph = LogInterp(E_grid, F[it, 0])
+                for rid in range(1, 18):
+                    val = S0[it, 0] * nr.get_cross_section(rid, E0) / fx["rate_photon_E0"][it]
+                    Eth = nucl._eth[rid]
+                    if Emax > Eth:
+                        knots = sorted(log(E) for E in E_grid if Eth < E < Emax)
+                        if rid == 15 and Eth < 5.412617347027785 < Emax:
+                            knots = sorted(knots + [log(5.412617347027785)])   # sign change of the closing polynomial (nucl.py:328)
+                        val += quad(lambda y: Fph(exp(y)) * exp(y) * nr.get_cross_section(rid, exp(y)), log(Eth), log(Emax),
+                                    epsrel=1e-12, epsabs=0, limit=2000, points=knots if knots else None)[0]
+                    pdi[it, rid - 1] = max(nucl.approx_zero, val)
+            mg = nucl.MatrixGenerator(T, {rid: pdi[:, rid - 1] for rid in range(1, 18)}, ii)
+            knotsT = [log(t) for t in T[1:-1]]
+            mpdi, mdcy = np.zeros((9, 9)), np.zeros((9, 9))
+            for i in range(9):
+                for j in range(9):
+                    if any(mg._pref_ij(nucl._rsig[rid], i, j) != 0 for rid in nucl._lrid):
+                        mpdi[i, j] = quad(lambda y: mg._pdi_kernel_ij(i, j, exp(y)) * exp(y), log(T[-1]), log(T[0]),
+                                          epsrel=1e-11, epsabs=0, limit=20000, points=knotsT)[0]
+                    if any(mg._pref_ij(nucl._dsig[did], i, j) != 0 for did in nucl._ldid):
+                        mdcy[i, j] = quad(lambda y: mg._dcy_kernel_ij(i, j, exp(y)) * exp(y), log(T[-1]), log(T[0]),
+                                          epsrel=1e-11, epsabs=0, limit=20000, points=knotsT)[0]
+        Y0 = ii.bbn_abundances()
+        Yf = fx["postd"] @ expm(mpdi + mdcy) @ fx["pred"] @ Y0
+        key = tag.replace("_tight", "")
+        out[key + "_pdi"], out[key + "_mpdi"], out[key + "_mdcy"], out[key + "_Yf"] = pdi, mpdi, mdcy, Yf
+    np.savez_compressed(os.path.join(OUT, "converged_reference.npz"), **out)
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 

@@ -302,3 +302,71 @@ def test_cfg5_resolution_heaviest_point(gpu_engine, xcheck_engine):
     A = np.array([1., 1., 2., 3., 3., 4., 6., 7., 7.])
     Y0 = m._sII.bbn_abundances()
     assert np.max(np.abs((A @ res[0]["Yf"][0]) / (A @ Y0) - 1.)) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: BenchmarkModel1/2, get_all_matp, flags.universal -- against fixtures generated from the reference
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag, cls", [("b1", "BenchmarkModel1"), ("b2", "BenchmarkModel2")])
+def test_benchmark_models_1_and_2(gpu_engine, tag, cls):
+    """BASELINE config 4 points: BenchmarkModel1/2(mchi=10, delta=1e-2, gammad=1e-3, gammav=1e-12) (ext/benchmarks.py:50-51)
+    through the model hooks, all stages against the reference at its defaults."""
+    import acropolis_b200.ext.benchmarks as bm
+    z = golden("resonance_%s_full.npz" % tag)
+    m = getattr(bm, cls)(mchi=10., delta=1e-2, gammad=1e-3, gammav=1e-12)
+    assert m._sTkd == pytest.approx(float(z["tempkd"]), rel=1e-8)
+    sp = m.point_spec()
+    assert np.array_equal(sp.E_grid, z["E_grid"]) and np.allclose(sp.T, z["T"], rtol=1e-14)
+XX
+    r = gpu_engine.run([sp], want=("F", "pdi", "mpdi", "mdcy", "Yf"))
+    assert relerr(r["F"].reshape(len(sp.T), 3, -1), z["F"]) < 1e-5
+    assert relerr(r["pdi"], z["pdi"], 1e-100) < 7e-4          # the reference's pdi quadrature noise at eps = 1e-3
+    assert relerr(r["mdcy"][0], z["mdcy"], 1e-100) < 1e-6
+    Yf = m.run_disintegration()
+    assert relerr(Yf, r["Yf"][0], 1e-30) < 1e-12
+    assert relerr(Yf, z["Yf"], 1e-30) < 1e-4
+
+
+def test_get_all_matp_vs_reference(gpu_engine):
+    """MatrixGenerator.get_all_matp (nucl.py:626-655): rate matrices integrated from Tmax down to every grid temperature,
+    on the reference's rates.  1e-5 against the reference with nucl.eps = 1e-9, 5e-4 against its default (eps = 1e-3: the
+    T-quadrature noise of the reference itself, 2e-4 between the two fixtures)."""
+    from acropolis_b200.nucl import MatrixGenerator, _lrid
+    from acropolis_b200.input import shared_input_interface
+    z = golden("cfg1_all_matp.npz")
+    grids = {rid: z["pdi"][:, rid - 1] for rid in _lrid}
+    T, (mp, md) = MatrixGenerator(z["T"], grids, shared_input_interface()).get_all_matp()
+    assert np.array_equal(T, z["T"]) and mp.shape == (len(T), 9, 9) and md.shape == (len(T), 9, 9)
+    assert np.all(mp[-1] == 0) and np.all(md[-1] == 0)          # T = Tmax: empty range
+    assert relerr(mp, z["all_mpdi_tight"], 1e-100) < 1e-5 and relerr(md, z["all_mdcy_tight"], 1e-100) < 1e-7
+    assert relerr(mp, z["all_mpdi"], 1e-100) < 5e-4 and relerr(md, z["all_mdcy"], 1e-100) < 1e-6
+
+
+def test_universal_spectrum_flag(gpu_engine):
+    """flags.universal (flags.py:33-41): universal photon spectrum instead of the cascade solution (cascade.py:774-812), pdi
+    integrals cut at min(E0, EC) (nucl.py:416-422); spectra, rates, matrices and abundances against the reference."""
+    import acropolis_b200.flags as flags
+    from acropolis_b200.models import DecayModel
+    from acropolis_b200.cascade import SpectrumGenerator
+    z = golden("universal.npz")
+    try:
+        flags.set_universal(True)
+        for tag in ("cfg1", "ee"):
+            m = DecayModel(*z[tag + "_ctor"])
+            sp = m.point_spec()
+            r = gpu_engine.run([sp], want=("F", "pdi", "mpdi", "mdcy", "Yf", "status"))
+            F = r["F"].reshape(len(sp.T), 3, -1)[:, 0]
+            assert relerr(F, z[tag + "_F"], 1e-190) < 1e-10
+            assert relerr(r["pdi"], z[tag + "_pdi"], 1e-100) < 7e-4        # reference pdi quadrature at eps = 1e-3
+            assert relerr(r["mdcy"][0], z[tag + "_mdcy"], 1e-100) < 1e-6
+            assert relerr(r["mpdi"][0], z[tag + "_mpdi"], 1e-100) < 2e-3
+            assert relerr(m.run_disintegration(), z[tag + "_Yf"], 1e-30) < 1e-4
+            # the reference-facing view (any offset) gives the same numbers
+            it = len(sp.T) // 2
+            u = SpectrumGenerator(m._sII).get_universal_spectrum(m._sE0, m._sS0, m._sSc, float(sp.T[it]), offset=5e-2)
+            assert relerr(u[1], z[tag + "_F"][it], 1e-190) < 1e-10
+    finally:
+        flags.set_universal(False)
+    # and the flag really switches: the cascade solution differs
+    r0 = gpu_engine.run([DecayModel(*z["cfg1_ctor"]).point_spec()], want=("pdi",))
+    assert relerr(r0["pdi"], z["cfg1_pdi"], 1e-100) > 1e-2
