@@ -861,10 +861,15 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
 #pragma unroll 1
             for (int k = 0; k < nq; ++k) {
                 const double fe = qw[k] * h * exp(fma(kap, fma(h, qx[k], m), bs));
-#pragma unroll 1
+                // the 17 table values of the node are requested together (L2-resident table, one coalesced line per
+                // reaction): with one load per trip of a rolled loop every FMA waited for its own load -- 27 % of the
+                // kernel's stall samples sat on this line (profiles/r02_ncu_solve_pdi_kernel_v1.txt)
+                double v[ACRO_NR];
+#pragma unroll
+                for (int r = 0; r < ACRO_NR; ++r) v[r] = sc[(int64_t)(k * ACRO_NR + r) * b.n_energy_total];
+#pragma unroll
                 for (int r = 0; r < ACRO_NR; ++r)
-                    if (open & (1u << r))
-                        accs[r * 32 + lane] = fma(fe, sc[(int64_t)(k * ACRO_NR + r) * b.n_energy_total], accs[r * 32 + lane]);
+                    if (open & (1u << r)) accs[r * 32 + lane] = fma(fe, v[r], accs[r * 32 + lane]);
             }
             continue;
         }

@@ -317,14 +317,18 @@ def test_benchmark_models_1_and_2(gpu_engine, tag, cls):
     assert m._sTkd == pytest.approx(float(z["tempkd"]), rel=1e-8)
     sp = m.point_spec()
     assert np.array_equal(sp.E_grid, z["E_grid"]) and np.allclose(sp.T, z["T"], rtol=1e-14)
-XX
+    # the model's source hooks: the reference averages sigma v with quad (ext/models.py:306-316, epsrel 1e-3: 1e-7 of noise),
+    # here a fixed-order rule (acropolis_b200/ext/models.py)
+    assert relerr(sp.S0, z["S0"], 1e-300) < 1e-6
     r = gpu_engine.run([sp], want=("F", "pdi", "mpdi", "mdcy", "Yf"))
     assert relerr(r["F"].reshape(len(sp.T), 3, -1), z["F"]) < 1e-5
     assert relerr(r["pdi"], z["pdi"], 1e-100) < 7e-4          # the reference's pdi quadrature noise at eps = 1e-3
     assert relerr(r["mdcy"][0], z["mdcy"], 1e-100) < 1e-6
     Yf = m.run_disintegration()
     assert relerr(Yf, r["Yf"][0], 1e-30) < 1e-12
-    assert relerr(Yf, z["Yf"], 1e-30) < 1e-4
+    # as for BenchmarkModel3 / cfg2: 1e-4 on the nuclides the reference's own T-quadrature noise (eps = 1e-3) does not
+    # dominate, 5e-4 on Li6 / Li7 (the tight-reference fixtures of the same model family hold 1e-6, test_gpu_parity.py)
+    assert relerr(Yf, z["Yf"], 1e-30) < 5e-4 and relerr(Yf[[1, 2, 4, 5]], z["Yf"][[1, 2, 4, 5]], 1e-30) < 1e-4
 
 
 def test_get_all_matp_vs_reference(gpu_engine):
