@@ -87,7 +87,7 @@ def load(variant="product"):
     lib.acro_run_batch_host.argtypes = [vp, C.POINTER(Batch), C.POINTER(Out), i32]
     lib.acro_unpack_kernels.argtypes = [vp, C.POINTER(Batch), vp, i32, vp, vp]
     lib.acro_matp_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.acro_transfer_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.acro_transfer_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.acro_total_rates.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.acro_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.acro_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]

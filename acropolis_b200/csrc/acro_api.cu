@@ -323,11 +323,11 @@ int acro_matp_batch(acro_handle_t* h, int32_t n_points, int32_t nt_max, const in
     return ACRO_OK;
 }
 
-int acro_transfer_batch(acro_handle_t* h, int32_t n, const double* mpdi, const double* mdcy, const double* factor,
-                        const double* t_at_tmax, double* expm_out, double* Yf, int32_t* status, void* stream) {
+int acro_transfer_batch(acro_handle_t* h, int32_t n, const double* mpdi, const double* mdcy, const int32_t* matrix_index,
+                        const double* factor, const double* t_at_tmax, double* expm_out, double* Yf, int32_t* status, void* stream) {
     if (!h || !mpdi || !mdcy || !t_at_tmax || !Yf) return ACRO_EINVAL;
     CU(h, cudaSetDevice(h->device));
-    CU(h, launch_transfer(n, mpdi, mdcy, factor, t_at_tmax, expm_out, Yf, status, h->tables, (cudaStream_t)stream, h->lc));
+    CU(h, launch_transfer(n, mpdi, mdcy, matrix_index, factor, t_at_tmax, expm_out, Yf, status, h->tables, (cudaStream_t)stream, h->lc));
     return ACRO_OK;
 }
 

@@ -50,7 +50,7 @@ cudaError_t launch_matrix(int n_points, const int32_t* pt_nt, const int32_t* pt_
                           const double* pdi, const double* T_lo, const double* pt_t_at_tmax, const int* status_sys,
                           const double* pt_e0, int nt_max, double* mpdi, double* mdcy, double* Yf, int32_t* status,
                           const DeviceTables& t, const acro_params_t& p, cudaStream_t st, LaunchCounters& lc);
-cudaError_t launch_transfer(int n, const double* mpdi, const double* mdcy, const double* factor, const double* t_at_tmax,
+cudaError_t launch_transfer(int n, const double* mpdi, const double* mdcy, const int32_t* matrix_index, const double* factor, const double* t_at_tmax,
                             double* expm_out, double* Yf, int32_t* status, const DeviceTables& t, cudaStream_t st,
                             LaunchCounters& lc);
 cudaError_t launch_total_rates(int n, const double* E, const double* T, double* out, const DeviceTables& t,

@@ -1207,6 +1207,7 @@ __global__ void __launch_bounds__(32) matrix_kernel(int n_points, const int32_t*
 }
 
 __global__ void __launch_bounds__(64) transfer_kernel(int n, const double* __restrict__ mpdi, const double* __restrict__ mdcy,
+                                                      const int32_t* __restrict__ matrix_index,
                                                       const double* __restrict__ factor, const double* __restrict__ t_at_tmax,
                                                       double* __restrict__ expm_out, double* __restrict__ Yf_out,
                                                       int32_t* __restrict__ status, DeviceTables t) {
@@ -1214,7 +1215,8 @@ __global__ void __launch_bounds__(64) transfer_kernel(int n, const double* __res
     if (i >= n) return;
     double A[81], Yf[27];
     const double f = factor ? factor[i] : 1.0;
-    for (int k = 0; k < 81; ++k) A[k] = f * mpdi[(int64_t)i * 81 + k] + mdcy[(int64_t)i * 81 + k];
+    const int64_t m = matrix_index ? matrix_index[i] : i;       // many rescalings of one (mpdi, mdcy) pair share its storage
+    for (int k = 0; k < 81; ++k) A[k] = f * mpdi[m * 81 + k] + mdcy[m * 81 + k];
     int bad = 0;
     apply_transfer(A, t_at_tmax[i], t.Y0, expm_out ? expm_out + (int64_t)i * 81 : nullptr, Yf, &bad);
     for (int k = 0; k < 27; ++k) Yf_out[(int64_t)i * 27 + k] = Yf[k];
@@ -1375,11 +1377,11 @@ cudaError_t launch_matrix(int n_points, const int32_t* pt_nt, const int32_t* pt_
     return cudaGetLastError();
 }
 
-cudaError_t launch_transfer(int n, const double* mpdi, const double* mdcy, const double* factor, const double* t_at_tmax,
+cudaError_t launch_transfer(int n, const double* mpdi, const double* mdcy, const int32_t* matrix_index, const double* factor, const double* t_at_tmax,
                             double* expm_out, double* Yf, int32_t* status, const DeviceTables& t, cudaStream_t st,
                             LaunchCounters& lc) {
     if (n == 0) return cudaSuccess;
-    transfer_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, mpdi, mdcy, factor, t_at_tmax, expm_out, Yf, status, t);
+    transfer_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, mpdi, mdcy, matrix_index, factor, t_at_tmax, expm_out, Yf, status, t);
     lc.launches++;
     return cudaGetLastError();
 }

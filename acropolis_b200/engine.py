@@ -489,24 +489,28 @@ class Engine(object):
             return out + (Yf.cpu().numpy().reshape(P, 9, 3), status.cpu().numpy())
         return out
 
-    def transfer(self, mpdi, mdcy, factor, t_at_tmax, want_expm=False):
-        """Fast-parameter path: Yf[n,9,3] = postd . expm(factor*mpdi + mdcy) . pred . Y0 (scans.py:106-107)."""
+    def transfer(self, mpdi, mdcy, factor, t_at_tmax, want_expm=False, index=None):
+        """Fast-parameter path: Yf[n,9,3] = postd . expm(factor*mpdi + mdcy) . pred . Y0 (scans.py:106-107).  With ``index``
+        (int[n]) job i uses the matrix pair index[i] of mpdi/mdcy [m,9,9]: the rescalings of one buffered pair share it."""
         dev = self.device
         mpdi = np.ascontiguousarray(mpdi, dtype=np.float64).reshape(-1, 81)
-        n = mpdi.shape[0]
+        mdcy = np.ascontiguousarray(mdcy, dtype=np.float64).reshape(-1, 81)
+        n = mpdi.shape[0] if index is None else len(index)
         d_mp = torch.from_numpy(mpdi.reshape(-1)).to(dev)
-        d_md = torch.from_numpy(np.ascontiguousarray(mdcy, dtype=np.float64).reshape(-1)).to(dev)
+        d_md = torch.from_numpy(mdcy.reshape(-1)).to(dev)
+        d_ix = torch.from_numpy(np.array(index, dtype=np.int32)).to(dev) if index is not None else None
         d_f = torch.from_numpy(np.array(np.broadcast_to(factor, (n,)), dtype=np.float64)).to(dev)
         d_t = torch.from_numpy(np.array(np.broadcast_to(t_at_tmax, (n,)), dtype=np.float64)).to(dev)
         Yf = torch.empty(n * 27, dtype=torch.float64, device=dev)
         ex = torch.empty(n * 81, dtype=torch.float64, device=dev) if want_expm else None
         status = torch.zeros(n, dtype=torch.int32, device=dev)
         torch.cuda.current_stream(dev).synchronize()
-        rc = self.lib.acro_transfer_batch(self.h, n, d_mp.data_ptr(), d_md.data_ptr(), d_f.data_ptr(), d_t.data_ptr(),
-                                          ex.data_ptr() if ex is not None else None, Yf.data_ptr(), status.data_ptr(),
-                                          self.stream.cuda_stream)
+        rc = self.lib.acro_transfer_batch(self.h, n, d_mp.data_ptr(), d_md.data_ptr(), d_ix.data_ptr() if d_ix is not None else None,
+                                          d_f.data_ptr(), d_t.data_ptr(), ex.data_ptr() if ex is not None else None, Yf.data_ptr(),
+                                          status.data_ptr(), self.stream.cuda_stream)
         self._check(rc, "acro_transfer_batch")
         self.stream.synchronize()
+        self.last_transfer_status = status.cpu().numpy()
         if want_expm:
             return Yf.cpu().numpy().reshape(n, 9, 3), ex.cpu().numpy().reshape(n, 9, 9)
         return Yf.cpu().numpy().reshape(n, 9, 3)

@@ -181,10 +181,11 @@ int acro_matp_batch(acro_handle_t* h, int32_t n_points, int32_t nt_max, const in
                     double* mpdi, double* mdcy, double* Yf, int32_t* status, void* stream);
 
 /* Fast-parameter path (scans.py:106-107,153-157; models.py:126-130): Yf = postd . expm(factor*mpdi + mdcy) . pred . Y0
- * for n matrices; mpdi/mdcy [n,9,9], factor [n], t_at_tmax [n]; device pointers.                               */
-int acro_transfer_batch(acro_handle_t* h, int32_t n, const double* mpdi, const double* mdcy, const double* factor,
-                        const double* t_at_tmax, double* expm_out /* [n,9,9] or NULL */, double* Yf, int32_t* status,
-                        void* stream);
+ * for n jobs; job i uses the matrix pair matrix_index[i] of mpdi/mdcy [m,9,9] (matrix_index NULL: pair i, m = n), so the
+ * many rescalings of one buffered pair share its storage; factor [n] (NULL: 1), t_at_tmax [n]; device pointers.       */
+int acro_transfer_batch(acro_handle_t* h, int32_t n, const double* mpdi, const double* mdcy, const int32_t* matrix_index,
+                        const double* factor, const double* t_at_tmax, double* expm_out /* [n,9,9] or NULL */, double* Yf,
+                        int32_t* status, void* stream);
 
 /* Total rates Gamma_X(E,T) for n arbitrary (E,T) pairs -> out[n,3] (SpectrumGenerator._rate_x, cascade.py:721-730). */
 int acro_total_rates(acro_handle_t* h, int32_t n, const double* E, const double* T, double* out, void* stream);
