@@ -57,7 +57,7 @@ class Out(C.Structure):
 EXPORTS = ("acro_abi_version", "acro_default_params", "acro_create", "acro_destroy", "acro_last_error", "acro_set_params",
            "acro_workspace_bytes", "acro_run_batch", "acro_run_batch_host", "acro_unpack_kernels", "acro_matp_batch",
            "acro_transfer_batch", "acro_total_rates", "acro_measure_fp64_peak", "acro_last_stage_ms", "acro_last_kernel_split_ms", "acro_launch_count",
-           "acro_count_work")
+           "acro_count_work", "acro_direct_rates")
 
 _libs = {}
 
@@ -89,6 +89,7 @@ def load(variant="product"):
     lib.acro_matp_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.acro_transfer_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.acro_total_rates.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.acro_direct_rates.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.acro_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.acro_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
     lib.acro_last_kernel_split_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]

@@ -345,6 +345,20 @@ int acro_total_rates(acro_handle_t* h, int32_t n, const double* E, const double*
     return ACRO_OK;
 }
 
+int acro_direct_rates(acro_handle_t* h, int32_t n, const double* E, const double* T, double* out, void* stream) {
+    if (!h || !E || !T || !out) return ACRO_EINVAL;
+    if (n <= 0) return ACRO_OK;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf items, counter;
+    CU(h, items.alloc(sizeof(DirectRateItem) * (size_t)n));
+    CU(h, counter.alloc(256));
+    CU(h, cudaMemsetAsync(counter.p, 0, 256, st));
+    CU(h, launch_direct_rate_table(n, E, T, out, h->tables, h->params, (DirectRateItem*)items.p, (int*)counter.p, st, h->lc));
+    CU(h, cudaStreamSynchronize(st));   // the temporaries die here
+    return ACRO_OK;
+}
+
 int acro_measure_fp64_peak(acro_handle_t* h, double* tflops) {
     if (!h || !tflops) return ACRO_EINVAL;
     CU(h, cudaSetDevice(h->device));

@@ -56,6 +56,9 @@ cudaError_t launch_transfer(int n, const double* mpdi, const double* mdcy, const
 cudaError_t launch_total_rates(int n, const double* E, const double* T, double* out, const DeviceTables& t,
                                const acro_params_t& p, DirectRateItem* items, int* item_count, cudaStream_t st,
                                LaunchCounters& lc);
+cudaError_t launch_direct_rate_table(int n, const double* E, const double* T, double* out, const DeviceTables& t,
+                                     const acro_params_t& p, DirectRateItem* items, int* item_count, cudaStream_t st,
+                                     LaunchCounters& lc);
 cudaError_t launch_unpack_kernels(const double* Kws, int64_t n_pairs_total, int64_t k_off, int ne, double* K_dense,
                                   cudaStream_t st, LaunchCounters& lc);
 cudaError_t run_dfma_benchmark(double* tflops, LaunchCounters& lc);

@@ -1238,6 +1238,19 @@ __global__ void total_rates_kernel(int n, const double* __restrict__ E, const do
     }
 }
 
+// the two tabulated rates as direct 2-D integrals for arbitrary (E,T) pairs -> out[n][3] = {pair creation, IC, IC}: what a
+// rates.db entry holds before log10 (tools/create_db.py:34-40 of the reference; the table generator tools/make_rates_db.py)
+__global__ void direct_rate_items_kernel(int n, const double* __restrict__ E, const double* __restrict__ T, double* __restrict__ out,
+                                         DirectRateItem* __restrict__ items, int* __restrict__ item_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[3 * (int64_t)i] = 0.0; out[3 * (int64_t)i + 1] = 0.0; out[3 * (int64_t)i + 2] = 0.0;
+    DirectRateItem it;
+    it.g_index = 3 * (int64_t)i; it.ne = 1; it.E = E[i]; it.T = T[i];
+    it.kind = 2 | (!(E[i] < kMe2 / (50.0 * T[i])) ? 1 : 0);        // pair-creation threshold (cascade.py:340)
+    items[atomicAdd(item_count, 1)] = it;
+}
+
 // DFMA throughput micro-benchmark: 8 independent chains per thread
 __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -1391,6 +1404,17 @@ cudaError_t launch_total_rates(int n, const double* E, const double* T, double* 
                                LaunchCounters& lc) {
     if (n == 0) return cudaSuccess;
     total_rates_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, E, T, out, t, p, items, item_count);
+    lc.launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_direct_rates(t, p, out, items, item_count, n, st, lc);
+}
+
+cudaError_t launch_direct_rate_table(int n, const double* E, const double* T, double* out, const DeviceTables& t,
+                                     const acro_params_t& p, DirectRateItem* items, int* item_count, cudaStream_t st,
+                                     LaunchCounters& lc) {
+    if (n == 0) return cudaSuccess;
+    direct_rate_items_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, E, T, out, items, item_count);
     lc.launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -459,6 +459,20 @@ class Engine(object):
                                               self.stream.cuda_stream), "acro_total_rates")
         return out.cpu().numpy().reshape(n, 3)
 
+    def direct_rates(self, E, T):
+        """The two tabulated rates as converged direct integrals for arrays of (E,T) -> [n,2] (pair creation, inverse
+        Compton): what rates.db stores before log10 (tools/make_rates_db.py)."""
+        self._sync_params()
+        E = np.ascontiguousarray(np.broadcast_arrays(E, T)[0], dtype=np.float64).reshape(-1)
+        T = np.ascontiguousarray(np.broadcast_to(T, E.shape), dtype=np.float64).reshape(-1)
+        n = E.shape[0]
+        dE, dT = torch.tensor(E, device=self.device), torch.tensor(T, device=self.device)
+        out = torch.empty(n * 3, dtype=torch.float64, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.lib.acro_direct_rates(self.h, n, dE.data_ptr(), dT.data_ptr(), out.data_ptr(), self.stream.cuda_stream),
+                    "acro_direct_rates")
+        return out.cpu().numpy().reshape(n, 3)[:, :2]
+
     def matp(self, T_list, pdi_list, T_lo=None, t_at_tmax=None, want_Yf=False):
         """MatrixGenerator.get_matp for several points: T_list[p] (NT_p,), pdi_list[p] (NT_p,17)."""
         self._sync_params()

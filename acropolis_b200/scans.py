@@ -63,6 +63,18 @@ def shard_indices(costs, n_shards):
     return [np.array(sorted(s), dtype=np.int64) for s in shards]
 
 
+def deal_snake(costs, n_shards):
+    """Deal items to shards heaviest first in snake order (0..n-1, n-1..0, ...): vectorised near-LPT -- every shard's load is
+    within one item of the mean for the smooth cost profile of a scan grid.  Returns a list of ascending index arrays that
+    partition range(len(costs))."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-costs, kind="stable")
+    k = np.arange(len(costs))
+    lap, pos = k // n_shards, k % n_shards
+    owner = np.where(lap % 2 == 0, pos, n_shards - 1 - pos)
+    return [np.sort(order[owner == r]) for r in range(n_shards)]
+
+
 def _dist_world():
     if os.environ.get("ACROPOLIS_B200_DIST", "1") == "0":
         return None
@@ -365,11 +377,30 @@ class BufferedScanner(object):
         return rows
 
     # -- no fast parameter: every point is a full computation (scans.py:110-124) -------------------------------
+    def _point_costs(self, pts):
+        """Cost proxy NT * NE^2 per grid point WITHOUT building models, for the classes whose injection energy is a
+        constructor parameter (DecayModel: mphi / 2, AnnihilationModel: mchi); None for any other class."""
+        from acropolis_b200.models import DecayModel, AnnihilationModel
+        key, scale, nt = {DecayModel: ("mphi", 0.5, 2. * params.NT_pd), AnnihilationModel: ("mchi", 1.0, 4. * params.NT_pd)}.get(
+            self._sModelClass, (None, None, None))
+        if key is None or not pts:
+            return None
+        src = np.array([p[key] for p in pts]) if key in pts[0] else np.full(len(pts), float(self._sFixed.get(key, np.nan)))
+        E0 = scale * src
+        if not np.all(np.isfinite(E0)):
+            return None
+        ne = np.where(E0 > params.Emin, np.maximum(np.floor(np.log10(np.maximum(E0, 1e-300) / params.Emin) * params.NE_pd), params.NE_min), 0.)
+        return nt * ne * ne + 1.0
+
     def _scan_plain(self, pts, rank, world, devices):
         N = len(pts)
         mine = np.arange(N)
-        if world > 1:   # cheap cost proxy before any model is built: the E0-dependent grid size is not known here,
-            mine = np.arange(rank, N, world)   # so deal points round-robin (neighbouring points cost the same)
+        if world > 1:
+            costs = self._point_costs(pts)
+            if costs is None:      # unknown model class: the grid size is not known before the model exists; neighbouring
+                mine = np.arange(rank, N, world)      # points cost about the same, so deal them round-robin
+            else:                  # heaviest first, dealt in snake order: every rank gets the same load to within one point
+                mine = deal_snake(costs, world)[rank]
         width = 2 + 9 * self._ncol()
         rows = (run_points(lambda **sp: self._build(sp), [pts[i] for i in mine], devices=devices).reshape(len(mine), width)
                 if len(mine) else np.zeros((0, width)))      # a rank without points still enters the gather

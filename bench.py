@@ -3,7 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W          # our arm (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the oracle port on all host threads
-    python bench.py --config {cfg1,cfg2,cfg3,cfg3b,cfg4,cfg5} ...    # the other BASELINE.json configs (default cfg3)
+    python bench.py --config {cfg1,cfg2,cfg3,cfg3b,cfg3scan,cfg4,cfg5} ...   # the other BASELINE.json configs (default cfg3)
 
 Default workload (BASELINE.json configs[2], SURVEY.md 8d "M3"): BufferedScanner(DecayModel, mphi=ScanParameter(0,3,200),
 tau=ScanParameter(3,10,200), temp0=10, n0a=1e-10, bree=0, braa=1) -- 40 000 points, all full computations.  The grid
@@ -56,6 +56,10 @@ WORKLOADS = {
     "cfg3b": dict(kind="fastscan", which="scan_decay_tau_aa",
                   text="cfg3b examples/scan_decay_tau_aa verbatim: DecayModel mphi(200) x n0a(200, fast) at tau=1e7 s: 200 full "
                        "points + 39 800 rescale-only points; step = the whole scan through BufferedScanner.perform_scan"),
+    "cfg3scan": dict(kind="fastscan", which="scan_decay_full",
+                     text="cfg3 as ONE call: BufferedScanner(DecayModel, mphi=ScanParameter(0,3,200), tau=ScanParameter(3,10,200), temp0=10, "
+                          "n0a=1e-10, bree=0, braa=1).perform_scan() -- 40 000 full points; under torchrun the points are dealt "
+                          "cost-balanced to the ranks and the rows all-gathered (strong scaling); step = the whole scan"),
     "cfg4": dict(kind="fastscan", which="scan_pwave_ee",
                  text="cfg4 examples/scan_pwave_ee verbatim: AnnihilationModel mchi(200) x b(200, fast), a=0, tempkd=1, bree=1: 200 "
                       "full + 39 800 rescale-only points, plus BenchmarkModel1-3 (ResonanceModel) points; step = the whole scan"),
@@ -624,6 +628,10 @@ def gpu_fastscan(args, w):
     if w["which"] == "scan_decay_tau_aa":      # examples/scan_decay_tau_aa:25-32
         mk = lambda: BufferedScanner(DecayModel, mphi=ScanParameter(0., 3., 200), tau=1e7, temp0=10.,
                                      n0a=ScanParameter(-14., -3., 200, fast=True), bree=0., braa=1.)
+        extra = None
+    elif w["which"] == "scan_decay_full":      # the benchmark scan (cfg3) through the public scan call
+        mk = lambda: BufferedScanner(DecayModel, mphi=ScanParameter(0., 3., 200), tau=ScanParameter(3., 10., 200), temp0=10.,
+                                     n0a=1e-10, bree=0., braa=1.)
         extra = None
     else:                                      # examples/scan_pwave_ee:25-32
         mk = lambda: BufferedScanner(AnnihilationModel, mchi=ScanParameter(0., 3., 200), a=0.,

@@ -190,6 +190,12 @@ int acro_transfer_batch(acro_handle_t* h, int32_t n, const double* mpdi, const d
 /* Total rates Gamma_X(E,T) for n arbitrary (E,T) pairs -> out[n,3] (SpectrumGenerator._rate_x, cascade.py:721-730). */
 int acro_total_rates(acro_handle_t* h, int32_t n, const double* E, const double* T, double* out, void* stream);
 
+/* The two TABULATED rates as converged direct 2-D integrals for n arbitrary (E,T) pairs -> out[n,3] = {thermal pair creation
+ * gamma gamma_th -> e+ e- (0 below its threshold E < me^2/(50T)), inverse Compton, inverse Compton}: the numbers a rates.db
+ * entry holds before log10 (reference tools/create_db.py:34-40, cascade.py:336-358,469-485).  tools/make_rates_db.py uses it
+ * to regenerate / extend the table on the GPU.  Synchronous on `stream`.                                            */
+int acro_direct_rates(acro_handle_t* h, int32_t n, const double* E, const double* T, double* out, void* stream);
+
 /* Measured FP64 FMA throughput of the device (DFMA micro-benchmark), in TFLOP/s; the roofline denominator of the
  * kernel builder.  Synchronous.                                                                                 */
 int acro_measure_fp64_peak(acro_handle_t* h, double* tflops);

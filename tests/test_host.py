@@ -194,6 +194,34 @@ def test_assemble_offsets():
     assert c["sc_mode"] == 0
 
 
+def test_deal_snake_partition_and_balance():
+    """Cost-balanced dealing of a plain scan to the ranks (BufferedScanner._scan_plain under torchrun)."""
+    from acropolis_b200.scans import deal_snake, BufferedScanner, ScanParameter
+    from acropolis_b200.models import DecayModel, AnnihilationModel
+    b = BufferedScanner(DecayModel, mphi=ScanParameter(0., 3., 40), tau=ScanParameter(3., 10., 30), temp0=10., n0a=1e-10, bree=0., braa=1.)
+    pts = b.scan_points()
+    costs = b._point_costs(pts)
+    assert costs.shape == (1200,) and costs.min() == 1.0          # below-threshold points cost (almost) nothing
+    for world in (2, 3, 8):
+        sh = deal_snake(costs, world)
+        assert sorted(np.concatenate(sh).tolist()) == list(range(1200))
+        loads = np.array([costs[x].sum() for x in sh])
+        assert loads.max() / loads.mean() < 1.02
+    # the proxy is the grid the model will really use
+    from acropolis_b200.engine import energy_grid
+    for i in (0, 400, 777, 1199):
+        m = b._build(pts[i])
+        ne = 0 if m.is_trivial() else len(energy_grid(m._sE0))
+        assert costs[i] == 40. * ne * ne + 1.
+    a = BufferedScanner(AnnihilationModel, mchi=ScanParameter(0., 3., 5), a=ScanParameter(-30., -25., 4), b=0., tempkd=1., bree=1., braa=0.)
+    assert a._point_costs(a.scan_points()).shape == (20,)
+
+    class Mine(DecayModel):
+        pass
+    assert BufferedScanner(Mine, mphi=ScanParameter(0., 3., 3), tau=ScanParameter(3., 10., 3), temp0=10., n0a=1e-10, bree=0.,
+                           braa=1.)._point_costs([dict(mphi=1., tau=1.)]) is None      # unknown class: round-robin
+
+
 def test_shard_indices_partition_and_balance():
     from acropolis_b200.scans import shard_indices, point_cost
     rng = np.random.default_rng(1)
