@@ -420,3 +420,19 @@ def test_scan_rows_are_savetxt_compatible(gpu_engine, tmp_path):
     assert np.array_equal(back, rows)
     # sorted-key column order (scans.py:122-124): b, mchi
     assert np.allclose(np.unique(rows[:, 0]), np.logspace(-20, -14, 4)) and np.allclose(np.unique(rows[:, 1]), np.logspace(0.5, 1.5, 3))
+
+
+def test_run_models_two_devices_one_process(gpu_engine):
+    """one process driving several GPUs (run_models(devices=[0, 1]): a ThreadPoolExecutor with one Engine
+    per device).  Function attributes (the 212 kB dynamic shared memory of kernels_mma_kernel) are per device, so the second
+    device used to fail with 'invalid argument'.  Needs two visible GPUs (gpurun --gpus 2)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from acropolis_b200.models import DecayModel
+    from acropolis_b200.scans import run_models
+    models = [DecayModel(m, t, 10., 1e-10, 0., 1.) for m in (4., 20., 150., 700.) for t in (1e4, 1e6, 1e8)]
+    one = run_models(models, devices=[0])
+    two = run_models(models, devices=[0, 1])
+    other = run_models(models, devices=[1])
+    assert np.array_equal(one, two) and np.array_equal(one, other)
