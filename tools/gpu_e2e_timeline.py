@@ -6,10 +6,12 @@ import acropolis_b200.flags as flags; flags.verbose = False
 from acropolis_b200.models import DecayModel
 from acropolis_b200.engine import Engine
 from acropolis_b200.scans import run_points
-from bench import grid_points, slice_params, FIXED
+import bench
 from functools import partial
-model = partial(DecayModel, **FIXED)
-pts = grid_points()
+W = bench.WORKLOADS["cfg3"]
+model = partial(DecayModel, **W["fixed"])
+pts = bench.grid_points(W)
+slice_params = lambda p, k: bench.slice_params(W, p, k)
 evs = []
 orig_launch = Engine.launch
 def launch(self, ch, stages=7 | 8):
