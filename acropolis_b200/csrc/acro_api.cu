@@ -21,6 +21,8 @@ struct acro_handle {
     LaunchCounters lc;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
+    void* host_arena = nullptr;        // device storage of acro_run_batch_host calls: grow-only, freed with the handle
+    size_t host_arena_bytes = 0;
 };
 
 static thread_local std::string g_create_err;
@@ -110,6 +112,7 @@ int acro_destroy(acro_handle_t* h) {
     if (!h) return ACRO_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_ratedb); cudaFree(h->d_cosmo_lT); cudaFree(h->d_cosmo_ld);
+    if (h->host_arena) cudaFree(h->host_arena);
     for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; ++i) if (h->lc.split[i]) cudaEventDestroy(h->lc.split[i]);
     delete h;
@@ -234,64 +237,84 @@ struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 8); }
-    cudaError_t upload(const void* src, size_t n, cudaStream_t st) {
-        cudaError_t e = alloc(n);
-        if (e != cudaSuccess || n == 0) return e;
-        return cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, st);
-    }
+};
+
+// bump allocator over the handle's host-path arena (256-byte aligned pieces)
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(char* b) : base(b) {}
+    static size_t al(size_t n) { return (n + 255) & ~(size_t)255; }
+    void* take(size_t n) { void* p = base ? base + off : nullptr; off += al(n ? n : 8); return p; }
 };
 }  // namespace
 
+// Host-pointer entry.  All device storage of a call (batch arrays, outputs, workspace) is carved out of ONE arena that the
+// handle keeps and only ever grows, so a loop over chunks pays cudaMalloc once (it used to allocate and
+// free ~25 buffers per call).  A batch whose workspace does not fit the device is refused with the size in the message:
+// split it (acro_workspace_bytes tells how large a sub-batch is; acropolis_b200/engine.py::Engine.chunks is the host-side
+// splitter the Python layer uses).
 int acro_run_batch_host(acro_handle_t* h, const acro_batch_t* hb, const acro_out_t* ho, int32_t stages) {
     if (!h || !hb || !ho) return ACRO_EINVAL;
     if (hb->n_points <= 0 || hb->n_systems <= 0) return ACRO_OK;
+    if (!hb->pt_pair_off) return fail(h, ACRO_EINVAL, "acro_run_batch_host: pt_pair_off is NULL");
     CU(h, cudaSetDevice(h->device));
     cudaStream_t st = nullptr;
     const size_t P = hb->n_points, S = hb->n_systems, NEt = hb->n_energy_total, NF = hb->n_sys_energy_total;
-    DevBuf pt_ne, pt_nt, pt_e_off, pt_sys_off, pt_pair_off, pt_e0, pt_tt, e_grid, sys_point, sys_T, sys_f_off, sys_k_off, s0, sc, sc_E;
-    DevBuf G, F, pdi, mpdi, mdcy, Yf, status, ws;
-    acro_batch_t db = *hb;
-    CU(h, pt_ne.upload(hb->pt_ne, P * 4, st));           db.pt_ne = (const int32_t*)pt_ne.p;
-    CU(h, pt_nt.upload(hb->pt_nt, P * 4, st));           db.pt_nt = (const int32_t*)pt_nt.p;
-    CU(h, pt_e_off.upload(hb->pt_e_off, P * 8, st));     db.pt_e_off = (const int64_t*)pt_e_off.p;
-    CU(h, pt_sys_off.upload(hb->pt_sys_off, P * 4, st)); db.pt_sys_off = (const int32_t*)pt_sys_off.p;
-    if (!hb->pt_pair_off) return fail(h, ACRO_EINVAL, "acro_run_batch_host: pt_pair_off is NULL");
-    CU(h, pt_pair_off.upload(hb->pt_pair_off, P * 8, st)); db.pt_pair_off = (const int64_t*)pt_pair_off.p;
-    CU(h, pt_e0.upload(hb->pt_e0, P * 8, st));           db.pt_e0 = (const double*)pt_e0.p;
-    CU(h, pt_tt.upload(hb->pt_t_at_tmax, P * 8, st));    db.pt_t_at_tmax = (const double*)pt_tt.p;
-    CU(h, e_grid.upload(hb->e_grid, NEt * 8, st));       db.e_grid = (const double*)e_grid.p;
-    CU(h, sys_point.upload(hb->sys_point, S * 4, st));   db.sys_point = (const int32_t*)sys_point.p;
-    CU(h, sys_T.upload(hb->sys_T, S * 8, st));           db.sys_T = (const double*)sys_T.p;
-    CU(h, sys_f_off.upload(hb->sys_f_off, S * 8, st));   db.sys_f_off = (const int64_t*)sys_f_off.p;
-    CU(h, sys_k_off.upload(hb->sys_k_off, S * 8, st));   db.sys_k_off = (const int64_t*)sys_k_off.p;
-    CU(h, s0.upload(hb->s0, S * 3 * 8, st));             db.s0 = (const double*)s0.p;
-    db.sc = nullptr; db.sc_E = nullptr;
-    if (hb->sc_mode == ACRO_SC_SEPARABLE) {
-        CU(h, sc.upload(hb->sc, S * 3 * 8, st));         db.sc = (const double*)sc.p;
-        CU(h, sc_E.upload(hb->sc_E, NEt * 3 * 8, st));   db.sc_E = (const double*)sc_E.p;
-    } else if (hb->sc_mode == ACRO_SC_DENSE) {
-        CU(h, sc.upload(hb->sc, NF * 3 * 8, st));        db.sc = (const double*)sc.p;
-    }
-    acro_out_t dout{};
-    CU(h, G.alloc(NF * 3 * 8));      dout.G = (double*)G.p;
-    if (ho->F) { CU(h, F.alloc(NF * 3 * 8)); dout.F = (double*)F.p; }
-    CU(h, pdi.alloc(S * ACRO_NR * 8)); dout.pdi = (double*)pdi.p;
-    CU(h, mpdi.alloc(P * 81 * 8));   dout.mpdi = (double*)mpdi.p;
-    CU(h, mdcy.alloc(P * 81 * 8));   dout.mdcy = (double*)mdcy.p;
-    CU(h, Yf.alloc(P * 27 * 8));     dout.Yf = (double*)Yf.p;
-    CU(h, status.alloc(P * 4));      dout.status = (int32_t*)status.p;
     const int64_t wsb = acro_workspace_bytes(h, hb);
-    CU(h, ws.alloc((size_t)wsb));
-    int rc = acro_run_batch(h, &db, &dout, ws.p, wsb, stages, st);
+    const size_t sc_bytes = hb->sc_mode == ACRO_SC_SEPARABLE ? S * 3 * 8 : (hb->sc_mode == ACRO_SC_DENSE ? NF * 3 * 8 : 0);
+    const size_t scE_bytes = hb->sc_mode == ACRO_SC_SEPARABLE ? NEt * 3 * 8 : 0;
+    acro_batch_t db = *hb;
+    acro_out_t dout{};
+    void *dF = nullptr, *ws = nullptr;
+    // two passes over the same carving sequence: sizes first, pointers second
+    for (int pass = 0; pass < 2; ++pass) {
+        Carver c(pass ? (char*)h->host_arena : nullptr);
+        db.pt_ne = (const int32_t*)c.take(P * 4);          db.pt_nt = (const int32_t*)c.take(P * 4);
+        db.pt_e_off = (const int64_t*)c.take(P * 8);       db.pt_sys_off = (const int32_t*)c.take(P * 4);
+        db.pt_pair_off = (const int64_t*)c.take(P * 8);    db.pt_e0 = (const double*)c.take(P * 8);
+        db.pt_t_at_tmax = (const double*)c.take(P * 8);    db.e_grid = (const double*)c.take(NEt * 8);
+        db.sys_point = (const int32_t*)c.take(S * 4);      db.sys_T = (const double*)c.take(S * 8);
+        db.sys_f_off = (const int64_t*)c.take(S * 8);      db.sys_k_off = (const int64_t*)c.take(S * 8);
+        db.s0 = (const double*)c.take(S * 3 * 8);
+        db.sc = sc_bytes ? (const double*)c.take(sc_bytes) : nullptr;
+        db.sc_E = scE_bytes ? (const double*)c.take(scE_bytes) : nullptr;
+        dout.G = (double*)c.take(NF * 3 * 8);
+        dF = ho->F ? c.take(NF * 3 * 8) : nullptr;         dout.F = (double*)dF;
+        dout.pdi = (double*)c.take(S * ACRO_NR * 8);       dout.mpdi = (double*)c.take(P * 81 * 8);
+        dout.mdcy = (double*)c.take(P * 81 * 8);           dout.Yf = (double*)c.take(P * 27 * 8);
+        dout.status = (int32_t*)c.take(P * 4);
+        ws = c.take((size_t)wsb);
+        if (pass == 0 && c.off > h->host_arena_bytes) {
+            size_t free_b = 0, total_b = 0;
+            CU(h, cudaMemGetInfo(&free_b, &total_b));
+            if (c.off > free_b + h->host_arena_bytes)
+                return fail(h, ACRO_ENOMEM, "acro_run_batch_host: the batch needs " + std::to_string(c.off >> 20) + " MiB of device memory (" +
+                            std::to_string((free_b + h->host_arena_bytes) >> 20) + " MiB available): split it into sub-batches");
+            if (h->host_arena) { cudaFree(h->host_arena); h->host_arena = nullptr; h->host_arena_bytes = 0; }
+            size_t want = c.off + c.off / 4;                       // 25 % headroom so that similar batches do not regrow it
+            if (want > free_b) want = c.off;
+            CU(h, cudaMalloc(&h->host_arena, want));
+            h->host_arena_bytes = want;
+        }
+    }
+#define UP(field, bytes) CU(h, cudaMemcpyAsync((void*)db.field, hb->field, (bytes), cudaMemcpyHostToDevice, st))
+    UP(pt_ne, P * 4); UP(pt_nt, P * 4); UP(pt_e_off, P * 8); UP(pt_sys_off, P * 4); UP(pt_pair_off, P * 8); UP(pt_e0, P * 8);
+    UP(pt_t_at_tmax, P * 8); UP(e_grid, NEt * 8); UP(sys_point, S * 4); UP(sys_T, S * 8); UP(sys_f_off, S * 8);
+    UP(sys_k_off, S * 8); UP(s0, S * 3 * 8);
+    if (sc_bytes) UP(sc, sc_bytes);
+    if (scE_bytes) UP(sc_E, scE_bytes);
+#undef UP
+    int rc = acro_run_batch(h, &db, &dout, ws, wsb, stages, st);
     if (rc) return rc;
-    if (ho->G && (stages & ACRO_STAGE_RATES)) CU(h, cudaMemcpyAsync(ho->G, G.p, NF * 3 * 8, cudaMemcpyDeviceToHost, st));
-    if (ho->F && (stages & ACRO_STAGE_SOLVE)) CU(h, cudaMemcpyAsync(ho->F, F.p, NF * 3 * 8, cudaMemcpyDeviceToHost, st));
-    if (ho->pdi && (stages & ACRO_STAGE_SOLVE)) CU(h, cudaMemcpyAsync(ho->pdi, pdi.p, S * ACRO_NR * 8, cudaMemcpyDeviceToHost, st));
+    if (ho->G && (stages & ACRO_STAGE_RATES)) CU(h, cudaMemcpyAsync(ho->G, dout.G, NF * 3 * 8, cudaMemcpyDeviceToHost, st));
+    if (ho->F && (stages & ACRO_STAGE_SOLVE)) CU(h, cudaMemcpyAsync(ho->F, dout.F, NF * 3 * 8, cudaMemcpyDeviceToHost, st));
+    if (ho->pdi && (stages & ACRO_STAGE_SOLVE)) CU(h, cudaMemcpyAsync(ho->pdi, dout.pdi, S * ACRO_NR * 8, cudaMemcpyDeviceToHost, st));
     if (stages & ACRO_STAGE_MATRIX) {
-        if (ho->mpdi) CU(h, cudaMemcpyAsync(ho->mpdi, mpdi.p, P * 81 * 8, cudaMemcpyDeviceToHost, st));
-        if (ho->mdcy) CU(h, cudaMemcpyAsync(ho->mdcy, mdcy.p, P * 81 * 8, cudaMemcpyDeviceToHost, st));
-        if (ho->Yf) CU(h, cudaMemcpyAsync(ho->Yf, Yf.p, P * 27 * 8, cudaMemcpyDeviceToHost, st));
-        if (ho->status) CU(h, cudaMemcpyAsync(ho->status, status.p, P * 4, cudaMemcpyDeviceToHost, st));
+        if (ho->mpdi) CU(h, cudaMemcpyAsync(ho->mpdi, dout.mpdi, P * 81 * 8, cudaMemcpyDeviceToHost, st));
+        if (ho->mdcy) CU(h, cudaMemcpyAsync(ho->mdcy, dout.mdcy, P * 81 * 8, cudaMemcpyDeviceToHost, st));
+        if (ho->Yf) CU(h, cudaMemcpyAsync(ho->Yf, dout.Yf, P * 27 * 8, cudaMemcpyDeviceToHost, st));
+        if (ho->status) CU(h, cudaMemcpyAsync(ho->status, dout.status, P * 4, cudaMemcpyDeviceToHost, st));
     }
     CU(h, cudaStreamSynchronize(st));
     return ACRO_OK;

@@ -277,6 +277,29 @@ def test_c_abi_host_entry(gpu_engine, results):
     rc = gpu_engine.lib.acro_run_batch_host(gpu_engine.h, C.byref(b), C.byref(o), _lib.STAGE_ALL)
     assert rc == 0, gpu_engine.lib.acro_last_error(gpu_engine.h)
     assert np.array_equal(Yf, r["Yf"]) and np.array_equal(pdi, r["pdi"]) and np.array_equal(F, r["F"].reshape(-1))
+    # a loop over calls reuses the handle's device arena (no allocation per call): same numbers, larger then smaller batches
+    for name in ("decay_big", "decay_nemin", "cfg1_decay"):
+        z2, sp2, r2 = results[name]
+        a2, cnt2 = gpu_engine.assemble([sp2])
+        b2 = _lib.Batch()
+        for k, v in cnt2.items():
+            setattr(b2, k, v)
+        for k in gpu_engine._ORDER:
+            setattr(b2, k, a2[k].ctypes.data if a2[k].nbytes else None)
+        Y2 = np.zeros((1, 9, 3))
+        o2 = _lib.Out()
+        o2.Yf = Y2.ctypes.data
+        assert gpu_engine.lib.acro_run_batch_host(gpu_engine.h, C.byref(b2), C.byref(o2), _lib.STAGE_ALL) == 0
+        assert np.array_equal(Y2, r2["Yf"])
+    # a batch that cannot fit the device is refused with its size in the message (no allocation attempt, no exit)
+    huge = _lib.Batch()
+    for k, v in cnt.items():
+        setattr(huge, k, v)
+    for k in gpu_engine._ORDER:
+        setattr(huge, k, a[k].ctypes.data if a[k].nbytes else None)
+    huge.n_pairs_total = 10**11
+    assert gpu_engine.lib.acro_run_batch_host(gpu_engine.h, C.byref(huge), C.byref(o), _lib.STAGE_ALL) == -3      # ACRO_ENOMEM
+    assert b"split it" in gpu_engine.lib.acro_last_error(gpu_engine.h)
     # error convention: bad arguments give a negative code and a message, never exit()
     b.ne_max = 1
     assert gpu_engine.lib.acro_run_batch_host(gpu_engine.h, C.byref(b), C.byref(o), _lib.STAGE_ALL) < 0

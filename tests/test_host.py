@@ -234,14 +234,14 @@ def test_shard_indices_partition_and_balance():
         assert loads.max() / loads.mean() < 1.02
 
 
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, port, q, n=11):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
-    from acropolis_b200.scans import gather_rows
+    from acropolis_b200.scans import gather_rows, deal_snake
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    n, width = 11, 29
-    mine = np.arange(rank, n, world)
+    width = 29
+    mine = deal_snake(np.arange(n, dtype=np.float64) + 1.0, world)[rank]      # the dealing perform_scan uses under torchrun
     rows = np.array([[i * 100.0 + c for c in range(width)] for i in mine]).reshape(len(mine), width)
     full = gather_rows(mine, rows, n, width)
     q.put((rank, full))
@@ -263,6 +263,23 @@ def test_gather_rows_gloo_world2():
         p.join(timeout=60)
     expect = np.array([[i * 100.0 + c for c in range(29)] for i in range(11)])
     assert np.array_equal(got[0], expect) and np.array_equal(got[1], expect)
+
+
+def test_gather_rows_gloo_with_an_empty_rank():
+    """more ranks than points -- the rank without points must still enter the gather (it used to raise in
+    reshape(0, -1) and leave the others hanging in all_gather).  World size 3, two rows."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 3, port, q, 2)) for r in range(3)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+    expect = np.array([[i * 100.0 + c for c in range(29)] for i in range(2)])
+    assert all(np.array_equal(got[r], expect) for r in range(3))
 
 
 def test_fsr_shape_matches_scalar_hook():
