@@ -1109,30 +1109,34 @@ __device__ __forceinline__ double pow10_segment(double alpha, double beta, doubl
     return ln10 * bot * dx * phi;
 }
 
-// One warp per point.  Integrates Gamma_r(T) T / |dT/dt| dlogT exactly: both factors are piecewise power laws
-// (log10-log10 linear on the NT-point rate grid, utils.py:38-61, and on the cosmo table, input.py:205-226), so
-// each sub-cell has the closed form of pow10_segment; no quadrature (the reference uses QAGS, nucl.py:613-614).
-__global__ void __launch_bounds__(32) matrix_kernel(int n_points, const int32_t* __restrict__ pt_nt,
-                                                    const int32_t* __restrict__ pt_sys_off, const double* __restrict__ sys_T,
-                                                    const double* __restrict__ pdi, const double* __restrict__ T_lo,
-                                                    const double* __restrict__ pt_t_at_tmax, const int* __restrict__ status_sys,
-                                                    const double* __restrict__ pt_e0, double* __restrict__ mpdi_out,
-                                                    double* __restrict__ mdcy_out, double* __restrict__ Yf_out,
-                                                    int32_t* __restrict__ status_out, DeviceTables t, acro_params_t p) {
+// One block per point: one warp when the batch has many points, eight warps when it has few (a single point would otherwise
+// spend 0.7 ms in ONE warp walking its ~2000 cosmo-table cells: half of the device latency of a run_disintegration() call).
+// Integrates Gamma_r(T) T / |dT/dt| dlogT exactly: both factors are piecewise power laws (log10-log10 linear on the NT-point
+// rate grid, utils.py:38-61, and on the cosmo table, input.py:205-226), so each sub-cell has the closed form of
+// pow10_segment; no quadrature (the reference uses QAGS, nucl.py:613-614).
+__global__ void __launch_bounds__(256) matrix_kernel(int n_points, const int32_t* __restrict__ pt_nt,
+                                                     const int32_t* __restrict__ pt_sys_off, const double* __restrict__ sys_T,
+                                                     const double* __restrict__ pdi, const double* __restrict__ T_lo,
+                                                     const double* __restrict__ pt_t_at_tmax, const int* __restrict__ status_sys,
+                                                     const double* __restrict__ pt_e0, double* __restrict__ mpdi_out,
+                                                     double* __restrict__ mdcy_out, double* __restrict__ Yf_out,
+                                                     int32_t* __restrict__ status_out, DeviceTables t, acro_params_t p) {
     extern __shared__ double sm[];
-    const int pt = blockIdx.x, lane = threadIdx.x;
+    __shared__ double s_part[8][ACRO_NR + 1];
+    __shared__ int s_st[8];
+    const int pt = blockIdx.x, tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
     if (pt >= n_points) return;
     const int nt = pt_nt[pt], s0 = pt_sys_off[pt];
     double* X = sm;             // [nt] log10 T
     double* Y = sm + nt;        // [17][nt] log10 rate
-    for (int k = lane; k < nt; k += 32) {
+    for (int k = tid; k < nt; k += nth) {
         X[k] = log10(sys_T[s0 + k]);
         for (int r = 0; r < ACRO_NR; ++r) Y[r * nt + k] = log10(pdi[(int64_t)(s0 + k) * ACRO_NR + r]);
     }
-    __syncwarp();
+    __syncthreads();
     int st = 0;
     if (status_sys)
-        for (int k = lane; k < nt; k += 32) st |= status_sys[s0 + k] ? ACRO_ST_DIRECT_RATE : 0;
+        for (int k = tid; k < nt; k += nth) st |= status_sys[s0 + k] ? ACRO_ST_DIRECT_RATE : 0;
     const double x_hi = X[nt - 1];
     double x_lo = X[0];
     if (T_lo) x_lo = fmin(fmax(log10(T_lo[pt]), X[0]), x_hi);
@@ -1151,7 +1155,7 @@ __global__ void __launch_bounds__(32) matrix_kernel(int n_points, const int32_t*
 #pragma unroll
     for (int r = 0; r <= ACRO_NR; ++r) acc[r] = 0.0;
     const double inv_dx = (double)(nt - 1) / (X[nt - 1] - X[0]);
-    for (int c = c_first + lane; c <= c_last; c += 32) {
+    for (int c = c_first + tid; c <= c_last; c += nth) {
         const double ca = fmax(LT[c + 1], x_lo), cb = fmin(LT[c], x_hi);
         if (!(cb > ca)) continue;
         const double mc = (LD[c + 1] - LD[c]) / (LT[c + 1] - LT[c]);
@@ -1177,7 +1181,21 @@ __global__ void __launch_bounds__(32) matrix_kernel(int n_points, const int32_t*
     for (int r = 0; r <= ACRO_NR; ++r) acc[r] = warp_sum(acc[r]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) st |= __shfl_xor_sync(0xffffffffu, st, o);
-    if (lane != 0) return;
+    if (nth > 32) {          // combine the warps in a fixed order (the result does not depend on scheduling)
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r <= ACRO_NR; ++r) s_part[warp][r] = acc[r];
+            s_st[warp] = st;
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (int w = 1; w < (nth >> 5); ++w) {
+#pragma unroll
+                for (int r = 0; r <= ACRO_NR; ++r) acc[r] += s_part[w][r];
+                st |= s_st[w];
+            }
+    }
+    if (tid != 0) return;
     double A[81], Mp[81], Md[81];
     for (int i = 0; i < 81; ++i) { Mp[i] = 0.0; Md[i] = 0.0; }
     // mpdi[i][j] = sum_r pref_r(i,j) I_r with I_r = int_{Tmin}^{Tmax} Gamma_r/|dT/dt| dT > 0: the reference integrates
@@ -1384,8 +1402,9 @@ cudaError_t launch_matrix(int n_points, const int32_t* pt_nt, const int32_t* pt_
         cudaError_t e = cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    matrix_kernel<<<n_points, 32, smem, st>>>(n_points, pt_nt, pt_sys_off, sys_T, pdi, T_lo, pt_t_at_tmax, status_sys, pt_e0,
-                                              mpdi, mdcy, Yf, status, t, p);
+    const int threads = n_points >= 2 * sm_count() ? 32 : 256;     // few points: eight warps share a point's cosmo cells
+    matrix_kernel<<<n_points, threads, smem, st>>>(n_points, pt_nt, pt_sys_off, sys_T, pdi, T_lo, pt_t_at_tmax, status_sys, pt_e0,
+                                                   mpdi, mdcy, Yf, status, t, p);
     lc.launches++;
     return cudaGetLastError();
 }
