@@ -829,61 +829,77 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
     const double* qw = c_glw + gl_offset(nq);
     double* accs = lnE + ne;             // [17][32] per-lane accumulators in shared memory (run-time reaction index)
     for (int r = 0; r < ACRO_NR; ++r) accs[r * 32 + lane] = 0.0;
-    // (A) cells that lie entirely above a reaction's threshold: nodes shared by all reactions
-    for (int c = lane; c < ne - 1; c += 32) {
-        const double y0 = lnE[c], y1 = lnE[c + 1];
-        const double hi = fmin(y1, lnEmax);
-        if (!(hi > y0)) continue;
-        const double ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
-        const double bs = lnF[c + 1] - ms * y1;
-        const double Elo = E[c];
-        const bool kink_cell = (Elo < kKink15 && kKink15 < E[c + 1]);   // reaction 15 is integrated separately there
-        // integrand = exp(kap y + bs) * sigma(e^y), kap = ms + 1.  Next to a floored spectrum value (e.g. F_gamma(E0) = 0
-        // for pure e+e- injection) kap reaches ~1e4 and the cell's weight sits within 1/|kap| of one end.  The cell is
-        // therefore cut, starting from its large end, into pieces over which the exponent changes by <= 2 (at most 40
-        // e-folds are kept: the rest is < e^-40 of the cell), each piece with the plain nq-point rule.  Ordinary cells
-        // (|kap| * width <= 2) are a single piece.
-        const double kap = ms + 1.0, width = hi - y0;
-        const double len = fmin(width, 40.0 / fmax(fabs(kap), 1e-300));
-        const int nsub = max(1, (int)ceil(0.5 * fabs(kap) * len));
-        const double piece = len / (double)nsub;
-        const double start = (kap > 0.0) ? hi - len : y0;      // pieces cover [start, start + len]
-        int r_hi = 0;                                          // reactions 0..r_hi-1 are open in this cell? (not sorted) -> mask
+    // (A) cells that lie entirely above a reaction's threshold: nodes shared by all reactions.  Lane = cell for the ordinary
+    //     cells; the few cells that need pieces or their own cross-section values are done by the whole warp together.
+    for (int c0 = 0; c0 < ne - 1; c0 += 32) {
+        const int c = c0 + lane;
+        bool coop = false;                                     // this lane's cell goes to the cooperative path below
+        double kap = 0.0, bs = 0.0, start = 0.0, piece = 0.0;
+        int nsub = 0;
         unsigned open = 0;
-        for (int r = 0; r < ACRO_NR; ++r)
-            if (kEth[r] <= Elo && !(r == 14 && kink_cell)) open |= 1u << r;
-        (void)r_hi;
-        if (!open) continue;
-        if (sig && nsub == 1 && hi == y1) {
-            // ordinary cell: node positions are the ones of pdi_sigma_kernel, cross-sections from the point's table
-            const double h = 0.5 * (y1 - y0), m = y0 + h;
-            const double* sc = sig + b.pt_e_off[pt] + c;
-#pragma unroll 1
-            for (int k = 0; k < nq; ++k) {
-                const double fe = qw[k] * h * exp(fma(kap, fma(h, qx[k], m), bs));
-                // the 17 table values of the node are requested together (L2-resident table, one coalesced line per
-                // reaction): with one load per trip of a rolled loop every FMA waited for its own load -- 27 % of the
-                // kernel's stall samples sat on this line (profiles/r02_ncu_solve_pdi_kernel_v1.txt)
-                double v[ACRO_NR];
-#pragma unroll
-                for (int r = 0; r < ACRO_NR; ++r) v[r] = sc[(int64_t)(k * ACRO_NR + r) * b.n_energy_total];
-#pragma unroll
+        if (c < ne - 1) {
+            const double y0 = lnE[c], y1 = lnE[c + 1];
+            const double hi = fmin(y1, lnEmax);
+            if (hi > y0) {
+                const double ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
+                bs = lnF[c + 1] - ms * y1;
+                const double Elo = E[c];
+                const bool kink_cell = (Elo < kKink15 && kKink15 < E[c + 1]);   // reaction 15 is integrated separately there
+                // integrand = exp(kap y + bs) * sigma(e^y), kap = ms + 1.  Next to a floored spectrum value (e.g. F_gamma(E0)
+                // = 0 for pure e+e- injection) kap reaches ~1e4 and the cell's weight sits within 1/|kap| of one end.  The
+                // cell is therefore cut, starting from its large end, into pieces over which the exponent changes by <= 2 (at
+                // most 40 e-folds are kept: the rest is < e^-40 of the cell), each piece with the plain nq-point rule.
+                // Ordinary cells (|kap| * width <= 2) are a single piece.
+                kap = ms + 1.0;
+                const double width = hi - y0;
+                const double len = fmin(width, 40.0 / fmax(fabs(kap), 1e-300));
+                nsub = max(1, (int)ceil(0.5 * fabs(kap) * len));
+                piece = len / (double)nsub;
+                start = (kap > 0.0) ? hi - len : y0;           // pieces cover [start, start + len]
                 for (int r = 0; r < ACRO_NR; ++r)
-                    if (open & (1u << r)) accs[r * 32 + lane] = fma(fe, v[r], accs[r * 32 + lane]);
-            }
-            continue;
-        }
-        for (int q = 0; q < nsub; ++q) {
-            const double a = start + piece * (double)q;
-            const double h = 0.5 * piece, m = a + h;
+                    if (kEth[r] <= Elo && !(r == 14 && kink_cell)) open |= 1u << r;
+                if (open && sig && nsub == 1 && hi == y1) {
+                    // ordinary cell: node positions are the ones of pdi_sigma_kernel, cross-sections from the point's table
+                    const double h = 0.5 * (y1 - y0), m = y0 + h;
+                    const double* sc = sig + b.pt_e_off[pt] + c;
 #pragma unroll 1
-            for (int k = 0; k < nq; ++k) {
+                    for (int k = 0; k < nq; ++k) {
+                        const double fe = qw[k] * h * exp(fma(kap, fma(h, qx[k], m), bs));
+                        // the 17 table values of the node are requested together (L2-resident table, one coalesced line per
+                        // reaction): with one load per trip of a rolled loop every FMA waited for its own load -- 27 % of the
+                        // kernel's stall samples sat on this line (profiles/r02_ncu_solve_pdi_kernel_v1.txt)
+                        double v[ACRO_NR];
+#pragma unroll
+                        for (int r = 0; r < ACRO_NR; ++r) v[r] = sc[(int64_t)(k * ACRO_NR + r) * b.n_energy_total];
+#pragma unroll
+                        for (int r = 0; r < ACRO_NR; ++r)
+                            if (open & (1u << r)) accs[r * 32 + lane] = fma(fe, v[r], accs[r * 32 + lane]);
+                    }
+                } else if (open) {
+                    coop = true;
+                }
+            }
+        }
+        // cells cut into pieces (up to 20 x nq nodes x 17 cross-sections: ~1 ms on one lane -- it WAS the solve stage of a
+        // single e+e- point, 1.1 of 2.0 ms device latency) and cells clipped by Emax: (piece, node) items dealt to the lanes
+        unsigned todo = __ballot_sync(0xffffffffu, coop);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const double kap_s = __shfl_sync(0xffffffffu, kap, src), bs_s = __shfl_sync(0xffffffffu, bs, src);
+            const double start_s = __shfl_sync(0xffffffffu, start, src), piece_s = __shfl_sync(0xffffffffu, piece, src);
+            const int nsub_s = __shfl_sync(0xffffffffu, nsub, src);
+            const unsigned open_s = __shfl_sync(0xffffffffu, open, src);
+            const double h = 0.5 * piece_s;
+            for (int it = lane; it < nsub_s * nq; it += 32) {
+                const int q = it / nq, k = it - q * nq;
+                const double m = start_s + piece_s * (double)q + h;
                 const double y  = fma(h, qx[k], m);
                 const double Ev = fexp(y);
-                const double fe = qw[k] * h * exp(fma(kap, y, bs));
+                const double fe = qw[k] * h * exp(fma(kap_s, y, bs_s));
 #pragma unroll 1
                 for (int r = 0; r < ACRO_NR; ++r)
-                    if (open & (1u << r)) accs[r * 32 + lane] = fma(fe, sigma_rt(r, Ev, y), accs[r * 32 + lane]);
+                    if (open_s & (1u << r)) accs[r * 32 + lane] = fma(fe, sigma_rt(r, Ev, y), accs[r * 32 + lane]);
             }
         }
     }
@@ -1319,7 +1335,10 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
         const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT + (kTileScalars + 1) * kTT +
                                               2 * kLogTab + kPanN * kPanN + (size_t)kMmWarps * MM_NCONST * 32);
         const int64_t passes_max = (tri_max + kMmPairs - 1) / kMmPairs;
-        dim3 grid((unsigned)((passes_max + kMmPassesPerBlock - 1) / kMmPassesPerBlock), (unsigned)b.n_points);
+        // passes of 512 pairs per block and Bose-table fill: 2 for scan batches (measured best: 1: 28.0, 2: 24.4, 4: 25.6 ms per
+        // slice); 1 when the whole batch would not even fill the SMs twice (single points: latency, not throughput)
+        const int ppb = (int64_t)b.n_points * passes_max < 4 * (int64_t)sm_count() ? 1 : kMmPassesPerBlock;
+        dim3 grid((unsigned)((passes_max + ppb - 1) / ppb), (unsigned)b.n_points);
         // function attributes are per device (each primary context has its own CUfunction): set before every launch
         cudaError_t e = cudaFuncSetAttribute(kernels_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1328,7 +1347,7 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
         lc.launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (lc.split[0]) cudaEventRecord(lc.split[0], st);
-        kernels_mma_kernel<<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p);
+        kernels_mma_kernel<<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p, ppb);
         lc.launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (lc.split[1]) lc.split_valid = cudaEventRecord(lc.split[1], st) == cudaSuccess;

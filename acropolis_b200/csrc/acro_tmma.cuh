@@ -164,13 +164,13 @@ __global__ void __launch_bounds__(128) pair_closed_forms_kernel(acro_batch_t b, 
 
 __global__ void __launch_bounds__(kMmThreads, 1) kernels_mma_kernel(acro_batch_t b, double* __restrict__ Kws,
                                                                     const double* __restrict__ closed, DeviceTables tb,
-                                                                    acro_params_t p) {
+                                                                    acro_params_t p, int passes_per_block) {
     extern __shared__ double sm[];
     const int pt = blockIdx.y;
     const int ne = b.pt_ne[pt], nt = b.pt_nt[pt], s0 = b.pt_sys_off[pt];
     const int64_t tri = (int64_t)ne * (ne + 1) / 2;
     const int passes = (int)((tri + kMmPairs - 1) / kMmPairs);
-    const int pass0 = blockIdx.x * kMmPassesPerBlock, pass_end = min(passes, pass0 + kMmPassesPerBlock);
+    const int pass0 = blockIdx.x * passes_per_block, pass_end = min(passes, pass0 + passes_per_block);
     if (pass0 >= passes) return;
     const double* eg = b.e_grid + b.pt_e_off[pt];
     const double Tmin = b.sys_T[s0], Tmax = b.sys_T[s0 + nt - 1];
