@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cmath>
+#include <algorithm>
 
 #include "acro_internal.h"
 #include "acro_physics.cuh"
@@ -1335,24 +1336,37 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
         const size_t smem = sizeof(double) * (3 * (size_t)kMaxPan * kPanN + (size_t)kMaxPan * kPanN * kTT + (kTileScalars + 1) * kTT +
                                               2 * kLogTab + kPanN * kPanN + (size_t)kMmWarps * MM_NCONST * 32);
         const int64_t passes_max = (tri_max + kMmPairs - 1) / kMmPairs;
-        // passes of 512 pairs per block and Bose-table fill: 2 for scan batches (measured best: 1: 28.0, 2: 24.4, 4: 25.6 ms per
-        // slice); 1 when the whole batch would not even fill the SMs twice (single points: latency, not throughput)
-        const int ppb = (int64_t)b.n_points * passes_max < 4 * (int64_t)sm_count() ? 1 : kMmPassesPerBlock;
+        // passes (32 pairs per warp) per block and Bose-table fill: up to kMmPassesPerBlock for scan batches (measured, 512
+        // threads, ms per 1000-point slice: 1: 28.5, 2: 24.8, 4: 22.9, 8: 19.8, 12: 19.6), fewer while that would leave less
+        // than two blocks per SM (single points and short batches: latency, not throughput)
+        const int ppb = (int)std::max<int64_t>(1, std::min<int64_t>(kMmPassesPerBlock, (int64_t)b.n_points * passes_max / (2 * (int64_t)sm_count())));
         dim3 grid((unsigned)((passes_max + ppb - 1) / ppb), (unsigned)b.n_points);
         // function attributes are per device (each primary context has its own CUfunction): set before every launch
-        cudaError_t e = cudaFuncSetAttribute(kernels_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        cudaError_t e = cudaSuccess;
+        // function attributes are per device (each primary context has its own CUfunction): set before every launch
+        if ((e = cudaFuncSetAttribute(kernels_mma_kernel<KIND_IC_PHOTON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(kernels_mma_kernel<KIND_IC_ELECTRON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(kernels_mma_kernel<KIND_PC_ELECTRON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         dim3 gp((unsigned)((tri_max + 127) / 128), (unsigned)b.n_points);
         pair_closed_forms_kernel<<<gp, 128, 0, st>>>(b, closed);
         lc.launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (lc.split[0]) cudaEventRecord(lc.split[0], st);
-        kernels_mma_kernel<<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p, ppb);
-        lc.launches++;
+        kernels_mma_kernel<KIND_IC_PHOTON><<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p, ppb);
+        kernels_mma_kernel<KIND_IC_ELECTRON><<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p, ppb);
+        kernels_mma_kernel<KIND_PC_ELECTRON><<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p, ppb);
+        lc.launches += 3;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (lc.split[1]) lc.split_valid = cudaEventRecord(lc.split[1], st) == cudaSuccess;
-        kernels_wien_kernel<64><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
+#if ACRO_WT_SPLIT
+        kernels_wien_kernel<64, KIND_IC_PHOTON><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
+        kernels_wien_kernel<64, KIND_IC_ELECTRON><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
+        kernels_wien_kernel<64, KIND_PC_ELECTRON><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
+        lc.launches += 3;
+#else
+        kernels_wien_kernel<64, -1><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
         lc.launches++;
+#endif
         return cudaGetLastError();
     }
 #ifdef ACRO_CROSSCHECK

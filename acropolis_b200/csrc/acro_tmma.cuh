@@ -36,20 +36,16 @@ constexpr int kMmThreads = ACRO_MM_THREADS;
 constexpr int kMmWarps = kMmThreads / 32;
 constexpr int kMmPairs = kMmWarps * 32;       // pairs per macro-pass of a block (32 per warp: phase A has lane = pair)
 #ifndef ACRO_MM_PASSES
-#define ACRO_MM_PASSES 2                      // macro-passes per block and Bose-table fill
+#define ACRO_MM_PASSES 12                     // macro-passes (32 pairs per warp each) per block and Bose-table fill
 #endif
 constexpr int kMmPassesPerBlock = ACRO_MM_PASSES;
-#ifndef ACRO_MM_MTILES
-#define ACRO_MM_MTILES 1                      // M-tiles (8 pairs each) a warp carries through the panel walk: 1 or 2
-#endif
-constexpr int kMmM = ACRO_MM_MTILES;
-static_assert(kMmM == 1 || kMmM == 2, "one or two M-tiles per warp");
 constexpr int kMmNT = kTT / 8;                // N-tiles (8 temperatures each)
 constexpr int kMmKS = kPanN / 4;              // k-steps (4 nodes each)
 static_assert(kTT % 8 == 0 && kPanN % 4 == 0, "tile and panel must split into DMMA 8x8x4 shapes");
 
-enum { MM_E = 0, MM_EP, MM_XA9, MM_XB9, MM_XA10, MM_XB10, MM_XA11, MM_XB11, MM_LA9, MM_LB9, MM_LA10, MM_LB10, MM_LA11, MM_LB11,
-       MM_CG, MM_CE, MM_BH, MM_PP, MM_C9, MM_C10, MM_I2EP, MM_FLAGS, MM_NCONST };   // MM_FLAGS: t_on[3] (8 bits each) | active << 24
+// per-pair constants of a warp's current 32 pairs in shared memory, [field][32]: energies, the limits of THIS launch's integral
+// and their logs, the photon kernel's c9, and MM_FLAGS = first served temperature of the tile | active << 8
+enum { MM_E = 0, MM_EP, MM_XA, MM_XB, MM_LA, MM_LB, MM_C9, MM_FLAGS, MM_NCONST };
 
 #ifndef ACRO_MM_ASM_VOLATILE
 #define ACRO_MM_ASM_VOLATILE 1
@@ -162,6 +158,12 @@ __global__ void __launch_bounds__(128) pair_closed_forms_kernel(acro_batch_t b, 
     closed[2 * npp + o] = !(Ep < E + kMe) ? bh_dsdE_Z2(E, Ep) : 0.0;        // the condition of pair_limits(): xa9 > 0
 }
 
+// One launch per integral kind (KIND = KIND_IC_PHOTON -> plane 1, KIND_IC_ELECTRON -> plane 4, KIND_PC_ELECTRON -> planes 3, 2
+// and the closed-form plane 0).  Three specialised kernels instead of one that loops over the kinds: the integrand is a
+// compile-time choice (no dispatch in the node loops, a third of the code per kernel), the pair constants shrink to 8 fields,
+// and the three launches together are 10 % faster than the fused kernel although each fills its own Bose table
+// (21.8 against 24.4 ms per 1000-point slice; with 2 passes per block, the fused kernel's optimum, the split form LOSES).
+template <int KIND>
 __global__ void __launch_bounds__(kMmThreads, 1) kernels_mma_kernel(acro_batch_t b, double* __restrict__ Kws,
                                                                     const double* __restrict__ closed, DeviceTables tb,
                                                                     acro_params_t p, int passes_per_block) {
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(kMmThreads, 1) kernels_mma_kernel(acro_batch_t
     const int64_t np = b.n_pairs_total;
     const int64_t c_off = b.pt_pair_off[pt], npp = b.n_pairs_points;
     const double a2 = kAlpha * kAlpha;
+    constexpr bool kEl = KIND == KIND_IC_ELECTRON;
 
     for (int t0 = 0; t0 < nt; t0 += kTT) {
         __syncthreads();
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(kMmThreads, 1) kernels_mma_kernel(acro_batch_t
         for (int pass = pass0; pass < pass_end; ++pass) {
             const int64_t loc0 = (int64_t)pass * kMmPairs + warp * 32;
             if (loc0 >= tri) continue;              // warp-uniform: nothing left for this warp
-            // ---- phase A: lane = pair: decode, limits, their logs, closed forms, first-served temperatures
+            // ---- phase A: lane = pair: decode, this integral's limits and their logs, first served temperature
             __syncwarp();
             {
                 const int64_t loc = loc0 + lane;
@@ -256,230 +259,150 @@ __global__ void __launch_bounds__(kMmThreads, 1) kernels_mma_kernel(acro_batch_t
                 }
                 const double E = eg[i], Ep = eg[j];
                 const PairLimits L = pair_limits(E, Ep);
-                const double r = E / fmax(Ep - E, 1e-300);
-                const double rr = E / Ep, gg_shape = 1.0 - rr + rr * rr;
+                const double xa = KIND == KIND_IC_PHOTON ? L.xa9 : (kEl ? L.xa10 : L.xa11);
+                const double xb = KIND == KIND_IC_PHOTON ? L.xb9 : (kEl ? L.xb10 : L.xb11);
                 cw[MM_E * 32 + lane] = E; cw[MM_EP * 32 + lane] = Ep;
-                cw[MM_XA9 * 32 + lane] = L.xa9; cw[MM_XB9 * 32 + lane] = L.xb9;
-                cw[MM_XA10 * 32 + lane] = L.xa10; cw[MM_XB10 * 32 + lane] = L.xb10;
-                cw[MM_XA11 * 32 + lane] = L.xa11; cw[MM_XB11 * 32 + lane] = L.xb11;
-                {
-                    const int64_t o = c_off + (active ? loc : 0);
-                    cw[MM_CG * 32 + lane] = closed[o];
-                    cw[MM_CE * 32 + lane] = closed[npp + o];
-                    cw[MM_BH * 32 + lane] = closed[2 * npp + o];
+                cw[MM_XA * 32 + lane] = xa; cw[MM_XB * 32 + lane] = xb;
+                cw[MM_LA * 32 + lane] = flog(fmax(xa, 1e-300));      // same calls as the other forms of the shared kernel
+                cw[MM_LB * 32 + lane] = flog(fmax(xb, 1e-300));
+                if (KIND == KIND_IC_PHOTON) {
+                    const double r = E / fmax(Ep - E, 1e-300);
+                    cw[MM_C9 * 32 + lane] = r * r / (2.0 + 2.0 * r);
                 }
-                cw[MM_PP * 32 + lane] = 1112.0 / (10125.0 * kPi) * (a2 * a2) / ((kMe2 * kMe2) * (kMe2 * kMe2)) * 8.0 * (kPi2 * kPi2) /
-                                        63.0 * (Ep * Ep) * (gg_shape * gg_shape);
-                cw[MM_C9 * 32 + lane] = r * r / (2.0 + 2.0 * r);
-                cw[MM_C10 * 32 + lane] = 0.25 * kMe2 / Ep;
-                cw[MM_I2EP * 32 + lane] = 0.5 / Ep;
-                int ton[3];
-#pragma unroll 1
-                for (int kind = 0; kind < 3; ++kind) {
-                    const double xa = kind == 0 ? L.xa9 : (kind == 1 ? L.xa10 : L.xa11);
-                    const double xb = kind == 0 ? L.xb9 : (kind == 1 ? L.xb10 : L.xb11);
-                    const bool has = active && (kind == KIND_PC_ELECTRON ? xb > xa : xa > 0.0);
-                    const bool reg = has && (deep || xa >= x_bot);
-                    // logs of the limits for the panel walk (same calls as the other forms of the shared kernel)
-                    cw[(MM_LA9 + 2 * kind) * 32 + lane] = flog(fmax(xa, 1e-300));
-                    cw[(MM_LB9 + 2 * kind) * 32 + lane] = flog(fmax(xb, 1e-300));
-                    // First temperature of the tile that the shared grid serves: the regime predicates (the expressions
-                    // kernels_wien_kernel evaluates on the same numbers) are monotone in T, which ascends with t.
-                    int lo = 0, hi = ntile;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        const bool on = fmin(xb, sT[4 * kTT + mid]) > xa && xa <= sT[5 * kTT + mid] &&
-                                        (kind != KIND_PC_ELECTRON || !(Ep < sT[6 * kTT + mid]));
-                        if (on) hi = mid; else lo = mid + 1;
-                    }
-                    const int v = reg ? lo : kTT;
-                    if (kind == 0) ton[0] = v; else if (kind == 1) ton[1] = v; else ton[2] = v;
+                // First temperature of the tile that the shared grid serves: the regime predicates (the expressions
+                // kernels_wien_kernel evaluates on the same numbers) are monotone in T, which ascends with t.
+                const bool has = active && (KIND == KIND_PC_ELECTRON ? xb > xa : xa > 0.0);
+                const bool reg = has && (deep || xa >= x_bot);
+                int lo = 0, hi = ntile;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const bool on = fmin(xb, sT[4 * kTT + mid]) > xa && xa <= sT[5 * kTT + mid] &&
+                                    (KIND != KIND_PC_ELECTRON || !(Ep < sT[6 * kTT + mid]));
+                    if (on) hi = mid; else lo = mid + 1;
                 }
-                cw[MM_FLAGS * 32 + lane] = (double)(ton[0] | (ton[1] << 8) | (ton[2] << 16) | ((active ? 1 : 0) << 24));
+                cw[MM_FLAGS * 32 + lane] = (double)((reg ? lo : kTT) | ((active ? 1 : 0) << 8));
             }
             __syncwarp();
-            // ---- phase B: sub-passes of 8 kMmM pairs; lane (g, q) owns pairs kMmM g ... kMmM g + kMmM - 1 of the sub-pass
+            // ---- phase B: four sub-passes of 8 pairs; lane (g, q) works for pair g of the sub-pass
 #pragma unroll 1
-            for (int sub = 0; sub < 4 / kMmM; ++sub) {
-                const int pp0 = sub * 8 * kMmM + kMmM * gq;    // slot 0; slot 1 = pp0 + 1
-                const int64_t loc = loc0 + pp0;
-                // both slots lie inside the system's padded triangle (engine: every system's plane block is padded to a
-                // multiple of 4 entries, so an odd last pair has a pad slot beside it; beyond that nothing may be written)
-                const bool st_ok = kMmM == 2 ? loc < ((tri + 3) & ~(int64_t)3) : loc < tri;
-                const int fl0 = (int)cw[MM_FLAGS * 32 + pp0], fl1 = kMmM == 2 ? (int)cw[MM_FLAGS * 32 + pp0 + 1] : 0;
-                const bool active0 = (fl0 >> 24) & 1, active1 = (fl1 >> 24) & 1;
-                double acc[kMmM][kMmNT][2];
-#pragma unroll 1
-                for (int kind = 0; kind < 3; ++kind) {
-                    // ---------------- the integral of this lane's two pairs on the shared grid, all temperatures of the tile
+            for (int sub = 0; sub < 4; ++sub) {
+                const int pp = sub * 8 + gq;
+                const int64_t loc = loc0 + pp;
+                const int fl = (int)cw[MM_FLAGS * 32 + pp];
+                const bool active = (fl >> 8) & 1;
+                const int ton = fl & 255;
+                const bool st_ok = loc < tri;
+                const double E = cw[MM_E * 32 + pp], Ep = cw[MM_EP * 32 + pp];
+                const double xa = cw[MM_XA * 32 + pp], xb = cw[MM_XB * 32 + pp];
+                const double lna = cw[MM_LA * 32 + pp], lnb = cw[MM_LB * 32 + pp];
+                double acc[kMmNT][2];
 #pragma unroll
-                    for (int s = 0; s < kMmM; ++s)
-#pragma unroll
-                        for (int n = 0; n < kMmNT; ++n) { acc[s][n][0] = 0.0; acc[s][n][1] = 0.0; }
-                    // walk parameters of the two slots, packed: first | last << 8 | part_lo << 16 | part_hi << 17 (first = 255: none)
-                    int wk0 = 255, wk1 = 255;
-#pragma unroll
-                    for (int s = 0; s < kMmM; ++s) {
-                        const int pp = pp0 + s;
-                        const double xa = cw[(MM_XA9 + 2 * kind) * 32 + pp], xb = cw[(MM_XB9 + 2 * kind) * 32 + pp];
-                        const double Ep = cw[MM_EP * 32 + pp];
-                        const bool active = s == 0 ? active0 : active1;
-                        const bool has = active && (kind == KIND_PC_ELECTRON ? xb > xa : xa > 0.0);
-                        const bool act = has && xb > xa && xa <= xa_max && (kind != KIND_PC_ELECTRON || !(Ep < pc_min));
-                        const double a = cw[(MM_LA9 + 2 * kind) * 32 + pp], bb = cw[(MM_LB9 + 2 * kind) * 32 + pp];
-                        int p_first = 255, p_last = 0, part = 0;
-                        if (act) {
-                            if (a <= g.y_bot) p_first = g.n_pan - 1;
-                            else { p_first = panel_of(g, a); part |= 1; }
-                            if (bb >= g.y_top) p_last = 0;
-                            else { p_last = panel_of(g, bb); part |= 2; }
-                            if (fmin(bb, g.y_top) <= fmax(a, g.y_bot)) p_first = 255;
-                        }
-                        const int wk = p_first | (p_last << 8) | (part << 16);
-                        if (s == 0) wk0 = wk; else wk1 = wk;
+                for (int n = 0; n < kMmNT; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+                // walk parameters: first (lowest) and last (highest) panel touched, which of them are cut by a limit
+                int p_first = -1, p_last = 0;
+                bool part_lo = false, part_hi = false;
+                {
+                    const bool has = active && (KIND == KIND_PC_ELECTRON ? xb > xa : xa > 0.0);
+                    const bool act = has && xb > xa && xa <= xa_max && (KIND != KIND_PC_ELECTRON || !(Ep < pc_min));
+                    if (act) {
+                        if (lna <= g.y_bot) p_first = g.n_pan - 1;
+                        else { p_first = panel_of(g, lna); part_lo = true; }
+                        if (lnb >= g.y_top) p_last = 0;
+                        else { p_last = panel_of(g, lnb); part_hi = true; }
+                        if (fmin(lnb, g.y_top) <= fmax(lna, g.y_bot)) p_first = -1;
                     }
-                    int p_lo = max((wk0 & 255) == 255 ? -1 : (wk0 & 255), (wk1 & 255) == 255 ? -1 : (wk1 & 255));
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) p_lo = max(p_lo, __shfl_xor_sync(0xffffffffu, p_lo, o));
-#pragma unroll 1
-                    for (int pn = p_lo; pn >= 0; --pn) {
-                        double lo, h;
-                        panel_geom(g, pn, lo, h);
-                        const int pf0 = wk0 & 255, pl0 = (wk0 >> 8) & 255, pf1 = wk1 & 255, pl1 = (wk1 >> 8) & 255;
-                        const bool in0 = pf0 != 255 && pn <= pf0 && pn >= pl0;
-                        const bool in1 = pf1 != 255 && pn <= pf1 && pn >= pl1;
-                        if (!__any_sync(0xffffffffu, in0 || in1)) continue;
-                        const bool lo0 = (wk0 >> 16) & 1, hi0 = (wk0 >> 17) & 1, lo1 = (wk1 >> 16) & 1, hi1 = (wk1 >> 17) & 1;
-                        const bool el = kind == KIND_IC_ELECTRON;
-                        const bool part0 = in0 && ((lo0 && pn == pf0) || (hi0 && pn == pl0) || (el && hi0 && pn == pl0 + 1));
-                        const bool part1 = in1 && ((lo1 && pn == pf1) || (hi1 && pn == pl1) || (el && hi1 && pn == pl1 + 1));
-                        const bool any_part = __any_sync(0xffffffffu, part0 || part1);
-                        const bool any_full = __any_sync(0xffffffffu, (in0 && !part0) || (in1 && !part1));
-                        const int base = pn * kPanN;
-                        double wA[kMmKS], wB[kMmKS];          // A fragments of slot 0 / slot 1 after the loop
-#pragma unroll
-                        for (int mm = 0; mm < kMmKS; ++mm) { wA[mm] = 0.0; wB[mm] = 0.0; }
-#pragma unroll 1
-                        for (int s = 0; s < kMmM; ++s) {
-#pragma unroll
-                            for (int mm = 0; mm < kMmKS; ++mm) wA[mm] = wB[mm];       // rotate: slot 0 ends up in wA (kMmM = 2)
-                            const int pp = pp0 + s;
-                            const bool in = s ? in1 : in0, part = s ? part1 : part0, full = in && !part;
-                            PairConst c;
-                            c.E = cw[MM_E * 32 + pp]; c.Ep = cw[MM_EP * 32 + pp]; c.dE = c.Ep - c.E;
-                            c.c9 = cw[MM_C9 * 32 + pp]; c.c10 = cw[MM_C10 * 32 + pp]; c.i2Ep = cw[MM_I2EP * 32 + pp];
+                }
+                PairConst c;
+                c.E = E; c.Ep = Ep; c.dE = Ep - E;
+                c.c9 = KIND == KIND_IC_PHOTON ? cw[MM_C9 * 32 + pp] : 0.0;
+                {
+                    const double iEp = frcp(Ep);
+                    c.c10 = 0.25 * kMe2 * iEp; c.i2Ep = 0.5 * iEp;
+                }
 #if ACRO_FQ_LOGTAB
-                            c.lt = s_lt;
+                c.lt = s_lt;
 #endif
-                            const double xa = cw[(MM_XA9 + 2 * kind) * 32 + pp];
-                            const double lna = cw[(MM_LA9 + 2 * kind) * 32 + pp];
-                            double w[kMmKS];
+#pragma unroll 1
+                for (int pn = __reduce_max_sync(0xffffffffu, p_first); pn >= 0; --pn) {
+                    double lo, h;
+                    panel_geom(g, pn, lo, h);
+                    const bool in = p_first >= 0 && pn <= p_first && pn >= p_last;
+                    if (!__any_sync(0xffffffffu, in)) continue;
+                    const bool part = in && ((part_lo && pn == p_first) || (part_hi && pn == p_last) || (kEl && part_hi && pn == p_last + 1));
+                    const bool full = in && !part;
+                    const bool any_part = __any_sync(0xffffffffu, part);
+                    const bool any_full = __any_sync(0xffffffffu, full);
+                    const int base = pn * kPanN;
+                    double w[kMmKS];          // this lane's A fragments: weights of nodes q, q+4, q+8 for its pair
 #pragma unroll
-                            for (int mm = 0; mm < kMmKS; ++mm) w[mm] = 0.0;
-                            if (any_part) {
-                                const int wk = s ? wk1 : wk0;
-                                const bool p_lo_s = (wk >> 16) & 1, p_hi_s = (wk >> 17) & 1;
-                                const int pf_s = wk & 255, pl_s = (wk >> 8) & 255;
-                                const double a_s = fmax(lna, g.y_bot), b_s = fmin(cw[(MM_LB9 + 2 * kind) * 32 + pp], g.y_top);
-                                const bool layer = el && p_hi_s;
-                                const double lo_y = (p_lo_s && pn == pf_s) ? a_s : lo;
-                                const double hi_y = (p_hi_s && pn == pl_s) ? b_s : lo + h;
-                                partial_panel_q(kind, c, xa, lna, part ? lo_y : lo, part ? hi_y : lo + h, lo, h,
-                                                layer ? b_s : hi_y + 2.0, q, part, s_modal, w);
-                            }
-                            if (any_full) {
-                                const double wscale = 0.5 * h;
+                    for (int mm = 0; mm < kMmKS; ++mm) w[mm] = 0.0;
+                    if (any_part) {
+                        const double a_s = fmax(lna, g.y_bot), b_s = fmin(lnb, g.y_top);
+                        const bool layer = kEl && part_hi;
+                        const double lo_y = (part_lo && pn == p_first) ? a_s : lo;
+                        const double hi_y = (part_hi && pn == p_last) ? b_s : lo + h;
+                        partial_panel_q(KIND, c, xa, lna, part ? lo_y : lo, part ? hi_y : lo + h, lo, h,
+                                        layer ? b_s : hi_y + 2.0, q, part, s_modal, w);
+                    }
+                    if (any_full) {
+                        const double wscale = 0.5 * h;
 #pragma unroll
-                                for (int mm = 0; mm < kMmKS; ++mm) {
-                                    const int m = q + 4 * mm;
-                                    const int k = base + m;
-                                    const double fv = node_core(kind, c, sx[k], six[k], sy[k], xa, lna) * (c_glw[gl_offset(kPanN) + m] * wscale);
-                                    if (full) w[mm] = fv;
-                                }
-                            }
-#pragma unroll
-                            for (int mm = 0; mm < kMmKS; ++mm) wB[mm] = w[mm];
-                        }
-                        // ---- the contraction over the panel's 12 nodes: 3 k-steps x 5 N-tiles x 2 M-tiles of DMMA.8x8x4
-#pragma unroll
-                        for (int ks = 0; ks < kMmKS; ++ks) {
-                            const double* __restrict__ Bk = sBq + (size_t)(base + q + 4 * ks) * kTT;
-#pragma unroll
-                            for (int n = 0; n < kMmNT; ++n) {
-                                const double bf = Bk[8 * n];
-                                if (kMmM == 2) {
-                                    dmma884(acc[0][n][0], acc[0][n][1], wA[ks], bf);
-                                    dmma884(acc[kMmM - 1][n][0], acc[kMmM - 1][n][1], wB[ks], bf);
-                                } else {
-                                    dmma884(acc[0][n][0], acc[0][n][1], wB[ks], bf);
-                                }
-                            }
+                        for (int mm = 0; mm < kMmKS; ++mm) {
+                            const int m = q + 4 * mm;
+                            const int k = base + m;
+                            const double fv = node_core(KIND, c, sx[k], six[k], sy[k], xa, lna) * (c_glw[gl_offset(kPanN) + m] * wscale);
+                            if (full) w[mm] = fv;
                         }
                     }
-                    // ---------------- epilogue: this lane holds I[pair 2g+s][t = 8 n + 2 q + e]
-                    const int ton0 = (fl0 >> (8 * kind)) & 255, ton1 = (fl1 >> (8 * kind)) & 255;
-                    const int pp1 = pp0 + kMmM - 1;             // slot 1 (= slot 0 for kMmM = 1)
-                    const double Ep0 = cw[MM_EP * 32 + pp0], Ep1 = cw[MM_EP * 32 + pp1];
-                    if (kind != KIND_PC_ELECTRON) {
-                        // ---- e -> gamma (plane 1), e -> e (plane 4)
-                        const double pre0 = 2.0 * kPi * a2 / (Ep0 * Ep0), pre1 = 2.0 * kPi * a2 / (Ep1 * Ep1);
-                        double* __restrict__ out = Kws + (kind == 0 ? 1 : 4) * np + loc;
+                    // ---- the contraction over the panel's 12 nodes: 3 k-steps x 5 N-tiles of DMMA.8x8x4
 #pragma unroll
-                        for (int n = 0; n < kMmNT; ++n)
+                    for (int ks = 0; ks < kMmKS; ++ks) {
+                        const double* __restrict__ Bk = sBq + (size_t)(base + q + 4 * ks) * kTT;
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int t = 8 * n + 2 * q + e;
-                                if (st_ok && t < ntile) {
-                                    double2 v;
-                                    v.x = (active0 && t >= ton0) ? pre0 * acc[0][n][e] : 0.0;
-                                    v.y = (active1 && t >= ton1) ? pre1 * acc[kMmM - 1][n][e] : 0.0;
-                                    if (kMmM == 2) *reinterpret_cast<double2*>(out + sK[t]) = v;
-                                    else out[sK[t]] = v.x;
-                                }
-                            }
-                    } else {
-                        // ---- gamma -> e-/e+ (planes 2, 3) and gamma -> gamma (plane 0)
-                        const double pre0 = 0.25 * kPi * a2 * kMe2 / (Ep0 * Ep0 * Ep0), pre1 = 0.25 * kPi * a2 * kMe2 / (Ep1 * Ep1 * Ep1);
-                        const double bh0 = cw[MM_BH * 32 + pp0], bh1 = cw[MM_BH * 32 + pp1];
-                        const double ce0 = cw[MM_CE * 32 + pp0], ce1 = cw[MM_CE * 32 + pp1];
-                        double* __restrict__ out = Kws + loc;
+                        for (int n = 0; n < kMmNT; ++n) dmma884(acc[n][0], acc[n][1], w[ks], Bk[8 * n]);
+                    }
+                }
+                // ---------------- epilogue: this lane holds I[pair g][t = 8 n + 2 q + e]
+                if (KIND != KIND_PC_ELECTRON) {
+                    // ---- e -> gamma (plane 1), e -> e (plane 4)
+                    const double pre = 2.0 * kPi * a2 / (Ep * Ep);
+                    double* __restrict__ out = Kws + (KIND == KIND_IC_PHOTON ? 1 : 4) * np + loc;
 #pragma unroll
-                        for (int n = 0; n < kMmNT; ++n)
+                    for (int n = 0; n < kMmNT; ++n)
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int t = 8 * n + 2 * q + e;
-                                if (st_ok && t < ntile) {
-                                    const double nz = sT[2 * kTT + t], dne = sT[kTT + t];
-                                    double2 pr, pm;
-                                    pr.x = fma(nz, bh0, (active0 && t >= ton0) ? pre0 * acc[0][n][e] : 0.0);
-                                    pr.y = fma(nz, bh1, (active1 && t >= ton1) ? pre1 * acc[kMmM - 1][n][e] : 0.0);
-                                    pm.x = fma(dne, ce0, pr.x);
-                                    pm.y = fma(dne, ce1, pr.y);
-                                    const int64_t o = sK[t];
-                                    if (kMmM == 2) {
-                                        *reinterpret_cast<double2*>(out + 3 * np + o) = pr;
-                                        *reinterpret_cast<double2*>(out + 2 * np + o) = pm;
-                                    } else {
-                                        out[3 * np + o] = pr.x;
-                                        out[2 * np + o] = pm.x;
-                                    }
-                                }
-                            }
-                        // plane 0 needs no accumulator: a rolled loop (one copy of exp instead of ten)
-                        const double pp_0 = cw[MM_PP * 32 + pp0], pp_1 = cw[MM_PP * 32 + pp1];
-                        const double cg0 = cw[MM_CG * 32 + pp0], cg1 = cw[MM_CG * 32 + pp1];
-#pragma unroll 1
-                        for (int ne2 = 0; ne2 < 2 * kMmNT; ++ne2) {
-                            const int t = 8 * (ne2 >> 1) + 2 * q + (ne2 & 1);
+                        for (int e = 0; e < 2; ++e) {
+                            const int t = 8 * n + 2 * q + e;
+                            if (st_ok && t < ntile) out[sK[t]] = (active && t >= ton) ? pre * acc[n][e] : 0.0;
+                        }
+                } else {
+                    // ---- gamma -> e-/e+ (planes 2, 3) and gamma -> gamma (plane 0); the pair's closed forms (Compton shapes,
+                    // Bethe-Heitler) come from the workspace block of pair_closed_forms_kernel
+                    const double pre = 0.25 * kPi * a2 * kMe2 / (Ep * Ep * Ep);
+                    const int64_t oc = c_off + (st_ok ? loc : 0);
+                    const double cg = closed[oc], ce = closed[npp + oc], bh = closed[2 * npp + oc];
+                    double* __restrict__ out = Kws + loc;
+#pragma unroll
+                    for (int n = 0; n < kMmNT; ++n)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int t = 8 * n + 2 * q + e;
                             if (st_ok && t < ntile) {
-                                const double mt = sT[7 * kTT + t], T6 = sT[3 * kTT + t], dne = sT[kTT + t];
-                                const double arg0 = Ep0 * mt, arg1 = Ep1 * mt;
-                                double2 v;
-                                v.x = fma(pp_0 * T6, arg0 > -700.0 ? fexp(arg0) : 0.0, dne * cg0);
-                                v.y = fma(pp_1 * T6, arg1 > -700.0 ? fexp(arg1) : 0.0, dne * cg1);
-                                if (kMmM == 2) *reinterpret_cast<double2*>(out + sK[t]) = v;
-                                else out[sK[t]] = v.x;
+                                const double pr = fma(sT[2 * kTT + t], bh, (active && t >= ton) ? pre * acc[n][e] : 0.0);
+                                const int64_t o = sK[t];
+                                out[3 * np + o] = pr;
+                                out[2 * np + o] = fma(sT[kTT + t], ce, pr);
                             }
+                        }
+                    // plane 0 needs no accumulator: a rolled loop (one copy of exp instead of ten)
+                    const double rr = E / Ep, gg_shape = 1.0 - rr + rr * rr;
+                    const double pp_pair = 1112.0 / (10125.0 * kPi) * (a2 * a2) / ((kMe2 * kMe2) * (kMe2 * kMe2)) * 8.0 * (kPi2 * kPi2) /
+                                           63.0 * (Ep * Ep) * (gg_shape * gg_shape);
+#pragma unroll 1
+                    for (int ne2 = 0; ne2 < 2 * kMmNT; ++ne2) {
+                        const int t = 8 * (ne2 >> 1) + 2 * q + (ne2 & 1);
+                        if (st_ok && t < ntile) {
+                            const double arg = Ep * sT[7 * kTT + t];
+                            out[sK[t]] = fma(pp_pair * sT[3 * kTT + t], arg > -700.0 ? fexp(arg) : 0.0, sT[kTT + t] * cg);
                         }
                     }
                 }

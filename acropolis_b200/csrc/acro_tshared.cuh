@@ -132,7 +132,7 @@ __device__ __forceinline__ int panel_of(const SharedGrid& g, double y) {   // pa
 // pools its items: exclusive prefix sum of the range lengths, then 32 items at a time, each lane fetching the constants
 // of the owning pair with shuffles.
 #ifndef ACRO_WT_MINBLOCKS
-#define ACRO_WT_MINBLOCKS 4
+#define ACRO_WT_MINBLOCKS 10
 #endif
 
 // first index t in [0, nt) with pred(T[t]) true, for a predicate that is false...false true...true along the grid
@@ -250,7 +250,10 @@ __device__ __forceinline__ void wien_pooled(const acro_batch_t& b, double* __res
     }
 }
 
-template <int Q>
+#ifndef ACRO_WT_SPLIT
+#define ACRO_WT_SPLIT 1          // 1: one launch per integral kind (KSEL = 0, 1, 2) instead of one launch for all three (KSEL = -1)
+#endif
+template <int Q, int KSEL>
 __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(acro_batch_t b, double* __restrict__ Kws,
                                                                                const double* __restrict__ closed, DeviceTables tb,
                                                                                acro_params_t p) {
@@ -303,16 +306,16 @@ __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(ac
         n = max(0, t_cut - t_lo);
     };
     int t_lo, n;
-    {   // e -> gamma
+    if (KSEL < 0 || KSEL == KIND_IC_PHOTON) {   // e -> gamma
         range(L.xa9, L.xb9, L.xa9 > 0.0, 0, t_lo, n);
         const double r = E / fmax(Ep - E, 1e-300);
         wien_pooled<KIND_IC_PHOTON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa9, L.xb9, r * r / (2.0 + 2.0 * r), 0.0, 0.0, 0.0, pre_ic, loc, lane, smask, spref, lt, tb);
     }
-    {   // e -> e
+    if (KSEL < 0 || KSEL == KIND_IC_ELECTRON) {   // e -> e
         range(L.xa10, L.xb10, L.xa10 > 0.0, 0, t_lo, n);
         wien_pooled<KIND_IC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa10, L.xb10, E, Ep - E, 0.25 * kMe2 / Ep, 0.5 / Ep, pre_ic, loc, lane, smask, spref, lt, tb);
     }
-    {   // gamma -> e (pair creation): needs E' >= me^2/(50 T)
+    if (KSEL < 0 || KSEL == KIND_PC_ELECTRON) {   // gamma -> e (pair creation): needs E' >= me^2/(50 T)
         const int t_pc = first_true(Tg, nt, [&](double T) { return !(Ep < kMe2 / (50.0 * T)); });
         range(L.xa11, L.xb11, true, t_pc, t_lo, n);
         const int64_t oc = b.pt_pair_off[pt] + locc;

@@ -67,12 +67,28 @@ def main(path, out_path):
         if short is None:
             continue
         launches.setdefault(short, {}).setdefault(int(r[ix["ID"]]), {})[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
-    n_slices = max(len(v) for v in launches.values())
+    n_slices = len(launches.get("kernels_mma_kernel") or max(launches.values(), key=len))
     trip = slice_triples(n_slices)
     kernels = {}
     for short, byid in launches.items():
         per = []
-        for k, (lid, m) in enumerate(sorted(byid.items())):
+        ordered = [m for _, m in sorted(byid.items())]
+        per_slice = max(1, len(ordered) // n_slices)       # a kernel launched several times per slice (one launch per integral
+        merged = []                                         # kind): its launches of one slice are summed
+        for k in range(n_slices):
+            grp = ordered[k * per_slice:(k + 1) * per_slice]
+            if not grp:
+                continue
+            tot = {}
+            dur = sum(g["gpu__time_duration.sum"] for g in grp)
+            for key in grp[0]:
+                if key.endswith(".sum"):
+                    tot[key] = sum(g.get(key, 0) for g in grp)
+                else:                                       # percentages: duration-weighted mean
+                    tot[key] = sum(g.get(key, 0) * g["gpu__time_duration.sum"] for g in grp) / dur
+            merged.append(tot)
+        for k, m in enumerate(merged):
+            lid = k
             flop = (2 * m.get("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", 0) + m.get("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", 0) +
                     m.get("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", 0) + 512 * m.get("sm__inst_executed_pipe_tensor_subpipe_dmma.sum", 0))
             per.append(dict(slice=k, triples=trip[k], flop=flop, flop_dmma=512 * m.get("sm__inst_executed_pipe_tensor_subpipe_dmma.sum", 0),
@@ -83,7 +99,7 @@ def main(path, out_path):
                             dram_read=m.get("dram__bytes_read.sum", 0), dram_write=m.get("dram__bytes_write.sum", 0)))
         n = len(per)
         mean = lambda key: sum(p[key] for p in per if p[key] is not None) / n
-        kernels[short] = dict(launches=n, flop_per_triple=sum(p["flop"] for p in per) / sum(p["triples"] for p in per),
+        kernels[short] = dict(launches=n, launches_per_slice=per_slice, flop_per_triple=sum(p["flop"] for p in per) / sum(p["triples"] for p in per),
                               flop_per_launch=mean("flop"), dmma_share_of_flop=(sum(p["flop_dmma"] for p in per) / max(sum(p["flop"] for p in per), 1)),
                               ms_under_ncu=mean("ms_under_ncu"), tflops_under_ncu=mean("flop") / (mean("ms_under_ncu") * 1e-3) / 1e12,
                               fp64_pipe_active_pct=mean("fp64_pipe_active_pct"), shared_pipe_active_pct=mean("shared_pipe_active_pct"),
