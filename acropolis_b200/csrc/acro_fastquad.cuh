@@ -38,6 +38,9 @@ __constant__ double c_lag_s[70];
 __constant__ double c_lag_w[70];
 __constant__ double c_lag_es[70];
 
+#ifndef ACRO_FQ_LAG_UNROLL
+#define ACRO_FQ_LAG_UNROLL 2
+#endif
 constexpr double kHalfRange = 8.0;              // log-range [e-folds] up to which Q/2 nodes are used (a9, a11 only)
 constexpr double kSteepX = 2.718281828459045;   // x_a/T above which the Laguerre form is used (u_a > 1)
 constexpr double kSteepSpan = 32.0;             // and the span (x_b - x_a)/T must exceed this (truncation e^-32)
@@ -201,8 +204,19 @@ __device__ __forceinline__ double integrand_core(const PairConst& c, double x, d
 // int_{x_a}^{x_b} core(x) * x^{P-1} / (pi^2 (e^{x/T}-1)) dx   with P = 2 (IC) or 1 (pair creation)
 // STEEP_ONLY: the caller guarantees x_a > e T (kernels_wien_kernel: x_a > wien_from T, wien_from >= e), so the plain
 // Gauss-Legendre branch is not instantiated
+//
+// x_kin (kernels_wien_kernel only): the kinematic upper limit of the integrand, x_kin >= x_b.  Where the range ends at the
+// thermal cut-off x_b = Ephb_T_max * T < x_kin (so x_a/T > Ephb_T_max - 32 = 168) the integrand stays analytic beyond x_b, and
+//     int_0^S f(s) e^{-s} ds  =  L[f from x_a] - e^{-S} L[f from x_b]
+// with the 4-node Gauss-Laguerre rule L on both (the order the long-span rule uses for x_a/T > e^4) is exact to 2e-13 for
+// S >= 2 (tools/proto/wien_short_span.py: 1500 random pairs per integral); for S < 2 an 8-node Gauss-Legendre rule on [0, S]
+// reaches 7e-13.  8 integrand evaluations instead of 32 -- these combinations are 4 % of the items of kernels_wien_kernel in
+// the benchmark scan but were 14 % of its nodes, run at half-empty warps.
+constexpr double kLag4Top = 9.395070912301133;   // largest node of the 4-point Gauss-Laguerre rule
+constexpr double kCutSplit = 2.0;
+
 template <int KIND, int Q, bool STEEP_ONLY = false>
-__device__ __forceinline__ double thermal_integral(const PairConst& c, double T, double x_a, double x_b) {
+__device__ __forceinline__ double thermal_integral(const PairConst& c, double T, double x_a, double x_b, double x_kin = -1.0) {
     const double iT = frcp(T);
     const double va = x_a * iT;
     if ((STEEP_ONLY || va > kSteepX) && (x_b - x_a) * iT >= kSteepSpan) {
@@ -218,6 +232,23 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
         else if (va > 4.4816890703380645) { n = 16; off = 30; }
         else { n = 24; off = 46; }
         double sum = 0.0;
+#if ACRO_FQ_LAG_UNROLL > 1
+        // all orders are even: two nodes per trip as independent chains (branch-free: a node beyond x_b is computed and
+        // dropped by a select, whatever its value)
+        double sum2 = 0.0;
+#pragma unroll 1
+        for (int kk = 0; kk < n; kk += 2) {
+            const int k = off + kk;
+            const double x0 = fma(c_lag_s[k], T, x_a), x1 = fma(c_lag_s[k + 1], T, x_a);
+            double g0 = integrand_core<KIND>(c, x0, x_a, 0.0, false), g1 = integrand_core<KIND>(c, x1, x_a, 0.0, false);
+            if (KIND != KIND_PC_ELECTRON) { g0 *= x0; g1 *= x1; }
+            const double a0 = fma(c_lag_w[k] * g0, frcp(fma(-Ea, c_lag_es[k], 1.0)), sum);
+            const double a1 = fma(c_lag_w[k + 1] * g1, frcp(fma(-Ea, c_lag_es[k + 1], 1.0)), sum2);
+            sum = x0 < x_b ? a0 : sum;
+            sum2 = x1 < x_b ? a1 : sum2;
+        }
+        sum += sum2;
+#else
 #pragma unroll 1
         for (int kk = 0; kk < n; ++kk) {
             const int k = off + kk;
@@ -228,6 +259,7 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
                 sum = fma(c_lag_w[k] * g, frcp(fma(-Ea, c_lag_es[k], 1.0)), sum);
             }
         }
+#endif
         return sum * T * Ea * (1.0 / kPi2);
     }
     if (STEEP_ONLY || va > kSteepX) {
@@ -237,6 +269,33 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
         const double Ea = fexp(-va);
         const double hs = 0.5 * S;
         double sum = 0.0;
+        if (STEEP_ONLY && x_b < x_kin && va > 54.598150033144236) {
+            if (S >= kCutSplit && fma(kLag4Top, T, x_b) < x_kin) {
+                const double eS = fexp(-S), Eb = Ea * eS;
+                double sum_b = 0.0;
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    const double x0 = fma(c_lag_s[k], T, x_a), x1 = fma(c_lag_s[k], T, x_b);
+                    double g0 = integrand_core<KIND>(c, x0, x_a, 0.0, false), g1 = integrand_core<KIND>(c, x1, x_a, 0.0, false);
+                    if (KIND != KIND_PC_ELECTRON) { g0 *= x0; g1 *= x1; }
+                    sum = fma(c_lag_w[k] * g0, frcp(fma(-Ea, c_lag_es[k], 1.0)), sum);
+                    sum_b = fma(c_lag_w[k] * g1, frcp(fma(-Eb, c_lag_es[k], 1.0)), sum_b);
+                }
+                return fma(-eS, sum_b, sum) * T * Ea * (1.0 / kPi2);
+            }
+            if (S < kCutSplit) {
+#pragma unroll 1
+                for (int k = 0; k < 8; ++k) {
+                    const double sk = fma(hs, c_glx[gl_offset(8) + k], hs);
+                    const double x = fma(sk, T, x_a);
+                    const double es = fexp(-sk);
+                    double g = integrand_core<KIND>(c, x, x_a, 0.0, false);
+                    if (KIND != KIND_PC_ELECTRON) g *= x;
+                    sum = fma(c_glw[gl_offset(8) + k] * g * es, frcp(fma(-Ea, es, 1.0)), sum);
+                }
+                return sum * hs * T * Ea * (1.0 / kPi2);
+            }
+        }
 #pragma unroll 1
         for (int k = 0; k < 32; ++k) {
             const double sk = fma(hs, c_glx[gl_offset(32) + k], hs);

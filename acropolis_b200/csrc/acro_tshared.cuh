@@ -175,18 +175,33 @@ __device__ __forceinline__ void wien_pooled(const acro_batch_t& b, double* __res
 #ifndef ACRO_WT_TWOPHASE
 #define ACRO_WT_TWOPHASE 1
 #endif
+    // "Short" for this scheduling = what takes the 32-node rule: the range ends at the KINEMATIC limit within 32 T of x_a (a span
+    // cut by the thermal limit 200 T costs 8 nodes, see thermal_integral).  Rare (0.14 % of the pair-creation items of the
+    // benchmark scan, none in the other two integrals) and monotone in T: a lane whose last temperature is long-span has no
+    // short item, and a warp without such a lane makes ONE pass with plain range masks (the classification only schedules
+    // the items; thermal_integral picks the rule from the same numbers itself).
+    auto is_short_at = [&](double T) { return !(x_b0 > p.Ephb_T_max * T) && !((x_b0 - x_a) >= kSteepSpan * T); };
+    const bool two_phase = ACRO_WT_TWOPHASE && __any_sync(0xffffffffu, n_mine > 0 && is_short_at(b.sys_T[s0 + max(t_hi - 1, 0)]));
 #pragma unroll 1
-    for (int phase = 0; phase < (ACRO_WT_TWOPHASE ? 2 : 1); ++phase) {
+    for (int phase = 0; phase < (two_phase ? 2 : 1); ++phase) {
     for (int c_lo = w_lo; c_lo < w_hi; c_lo += kWienChunk) {
         const int nc = min(kWienChunk, w_hi - c_lo);
         // masks and their prefix (lane tt handles temperature c_lo+tt and c_lo+32+tt)
         __syncwarp();
-        for (int tt = 0; tt < nc; ++tt) {
-            const int t = c_lo + tt;
-            const double T = b.sys_T[s0 + t];
-            const bool is_short = !((fmin(x_b0, p.Ephb_T_max * T) - x_a) >= kSteepSpan * T);
-            const unsigned m = __ballot_sync(0xffffffffu, t >= t_lo && t < t_hi && (!ACRO_WT_TWOPHASE || is_short == (phase == 1)));
-            if (lane == 0) smask[tt] = m;
+        if (!two_phase) {
+#pragma unroll 4
+            for (int tt = 0; tt < nc; ++tt) {
+                const int t = c_lo + tt;
+                const unsigned m = __ballot_sync(0xffffffffu, t >= t_lo && t < t_hi);
+                if (lane == 0) smask[tt] = m;
+            }
+        } else {
+            for (int tt = 0; tt < nc; ++tt) {
+                const int t = c_lo + tt;
+                const bool is_short = is_short_at(b.sys_T[s0 + t]);
+                const unsigned m = __ballot_sync(0xffffffffu, t >= t_lo && t < t_hi && is_short == (phase == 1));
+                if (lane == 0) smask[tt] = m;
+            }
         }
         __syncwarp();
         int cnt0 = (lane < nc) ? __popc(smask[lane]) : 0;
@@ -232,7 +247,7 @@ __device__ __forceinline__ void wien_pooled(const acro_batch_t& b, double* __res
                 else if (KIND == KIND_IC_ELECTRON) { c.E = o_c0; c.dE = o_c1; c.c10 = o_c2; c.i2Ep = o_c3; }
                 else { c.E = o_c0; c.Ep = o_c1; }
                 const int64_t o = b.sys_k_off[s0 + t] + o_loc;
-                const double v = o_pre * thermal_integral<KIND, Q, true>(c, T, o_xa, ulim);
+                const double v = o_pre * thermal_integral<KIND, Q, true>(c, T, o_xa, ulim, o_xb0);
                 if (KIND == KIND_IC_PHOTON) Kws[1 * np + o] = v;
                 else if (KIND == KIND_IC_ELECTRON) Kws[4 * np + o] = v;
                 else {
