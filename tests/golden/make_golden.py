@@ -535,6 +535,42 @@ def case_converged():
     np.savez_compressed(os.path.join(OUT, "converged_reference.npz"), **out)
 
 
+def case_scan_deviations():
+    """Consumer side of the scan rows (plots.py:40-101): abundance deviations in sigma for the committed reference scan rows
+    (scan_decay_5x5.npz, scan_fast.npz) against each observation set of obs.py.  matplotlib is absent in this image and
+    plots.py imports it at module level, so empty stand-in modules are registered first (nothing of them is called by
+    _get_abundance/_get_deviations)."""
+    import types
+    import numpy as np
+    mpl = types.ModuleType("matplotlib")
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.rc = lambda *a, **k: None
+    plt.rcParams = {}
+    tick = types.ModuleType("matplotlib.ticker")
+    tick.FixedLocator = tick.FixedFormatter = object
+    mpl.pyplot, mpl.ticker = plt, tick
+    sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt, "matplotlib.ticker": tick})
+    _import_reference()
+    import acropolis.plots as rp
+    import acropolis.obs as ro
+    out = {}
+    rows = {"decay5x5": np.load(os.path.join(OUT, "scan_decay_5x5.npz"))["rows"],
+            "fast_decay": np.load(os.path.join(OUT, "scan_fast.npz"))["decay_rows"],
+            "fast_annih": np.load(os.path.join(OUT, "scan_fast.npz"))["annih_rows"]}
+    for tag, data in rows.items():
+        for i in range(9):
+            m, d = rp._get_abundance(data, i)
+            out["%s_abundance_%d" % (tag, i)] = np.array([m, d])
+        for oname in ("pdg2020", "pdg2021", "pdg2022", "pdg2023", "pdg2024", "pdg"):
+            with np.errstate(all="ignore"):
+                out["%s_%s" % (tag, oname)] = np.array(rp._get_deviations(data.copy(), getattr(ro, oname)))
+    out["obs_table"] = np.array([[getattr(ro, o)[k].mean, getattr(ro, o)[k].err] for o in ("pdg2020", "pdg2021", "pdg2022", "pdg2023", "pdg2024")
+                                 for k in ("Yp", "DH", "HeD", "LiH")])
+    out["tex"] = np.array([rp.tex_title(mphi=10., tau=1e5, temp0=10., n0a=1e-10), rp.tex_label("mchi"), rp.tex_label("n0a"),
+                           rp.tex_label("nokey"), rp.tex_title(mchi=10., b=1e-20, tempkd=1.), rp.tex_title(braa=1)])
+    np.savez_compressed(os.path.join(OUT, "scan_deviations.npz"), **out)
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 

@@ -419,3 +419,55 @@ def test_annihilation_point_specs_equal_the_per_model_ones():
             assert (a is None) == (b is None), name
             if a is not None:
                 assert np.array_equal(np.asarray(a), np.asarray(b)), name
+
+
+# ---- consumer side of the scan rows: plots.py / obs.py numbers ---------------------------------
+
+def test_scan_deviations_match_reference():
+    """_get_abundance/_get_deviations on the committed reference scan rows against what the reference's plots.py returned for
+    them (tests/golden/make_golden.py case scan_deviations), every observation set of obs.py; labels as the reference's."""
+    import acropolis_b200.plots as plots
+    import acropolis_b200.obs as obs
+    z = np.load(os.path.join(GOLDEN, "scan_deviations.npz"))
+    rows = {"decay5x5": np.load(os.path.join(GOLDEN, "scan_decay_5x5.npz"))["rows"],
+            "fast_decay": np.load(os.path.join(GOLDEN, "scan_fast.npz"))["decay_rows"],
+            "fast_annih": np.load(os.path.join(GOLDEN, "scan_fast.npz"))["annih_rows"]}
+    sets = ("pdg2020", "pdg2021", "pdg2022", "pdg2023", "pdg2024")
+    table = np.array([[getattr(obs, o)[k].mean, getattr(obs, o)[k].err] for o in sets for k in ("Yp", "DH", "HeD", "LiH")])
+    assert np.array_equal(table, z["obs_table"]) and obs.pdg is obs.pdg2024
+    for tag, data in rows.items():
+        for i in range(9):
+            assert np.array_equal(np.array(plots._get_abundance(data, i)), z["%s_abundance_%d" % (tag, i)])
+        for o in sets + ("pdg",):
+            got = np.array(plots._get_deviations(data.copy(), getattr(obs, o)))
+            assert np.allclose(got, z["%s_%s" % (tag, o)], rtol=1e-13, atol=0, equal_nan=True), (tag, o)
+    tex = [plots.tex_title(mphi=10., tau=1e5, temp0=10., n0a=1e-10), plots.tex_label("mchi"), plots.tex_label("n0a"),
+           plots.tex_label("nokey"), plots.tex_title(mchi=10., b=1e-20, tempkd=1.), plots.tex_title(braa=1)]
+    assert tex == [str(t) for t in z["tex"]]
+
+
+def test_scan_deviations_grid_and_exclusion():
+    """scan_deviations(): shapes follow the slow-parameter-first row order, 'overall' combines |D/H|, |Yp| and the one-sided
+    He3/D, fix_helium closes holes down a column, and a table without hydrogen maps to D/H = -10."""
+    import acropolis_b200.plots as plots
+    data = np.load(os.path.join(GOLDEN, "scan_fast.npz"))["decay_rows"]          # 4 mphi x 8 n0a
+    d = plots.scan_deviations(data)
+    assert d["x"].shape == (4, 8) and np.all(d["x"][:, 0] == d["x"][:, -1]) and np.all(d["y"][0] == d["y"][-1])
+    assert np.array_equal(d["overall"], np.maximum(np.maximum(np.abs(d["DH"]), np.abs(d["Yp"])), d["HeD"]))
+    assert np.array_equal(d["excluded"], d["overall"] > 1.95996)
+    # n0a = 1e-3 destroys everything once E0 = mphi/2 is above the D threshold (the two heavier masses), 1e-14 nothing
+    assert d["excluded"][2:, -1].all() and not d["excluded"][:2].any() and not d["excluded"][:, 0].any()
+    H = np.array([[0., 3., 1., 3., 1.], [0., 0., 3., 0., 0.]]).T                  # columns = fixed second parameter
+    F = plots._fix_helium(H.copy())
+    assert np.array_equal(F[:, 0], [0., 3., 10., 3., 10.]) and np.array_equal(F[:, 1], [0., 0., 3., 10., 10.])
+    empty = data.copy()
+    empty[:, 2:] = 0.
+    with np.errstate(all="ignore"):
+        Yp, DH, HeD, LiH = plots._get_deviations(empty, plots.pdg2022)
+    assert np.all(DH == -10) and np.all(np.isnan(HeD))        # as the reference: only D/H is repaired (plots.py:96-98)
+    nod = data.copy()
+    nod[:, [4, 13, 22]] = 0.                                   # no deuterium left: D/H below its error -> He3/D excluded
+    with np.errstate(all="ignore"):
+        assert np.all(plots._get_deviations(nod, plots.pdg2022)[2] == 10)
+    with pytest.raises(ImportError, match="matplotlib"):
+        plots.plot_scan_results(data)
