@@ -15,8 +15,8 @@ STAGE_RATES, STAGE_KERNELS, STAGE_SOLVE, STAGE_MATRIX, STAGE_ALL = 1, 2, 4, 8, 1
 ST_NONFINITE, ST_T_OUTSIDE, ST_DIRECT_RATE, ST_E0_ABOVE_GEV = 1, 2, 4, 8
 SC_NONE, SC_SEPARABLE, SC_DENSE = 0, 1, 2
 KERNELS_FAST, KERNELS_PLAIN_GL, KERNELS_PER_T = 0, 1, 2
-ABI_VERSION = 3
-KERNEL_SPLIT_NAMES = ("pair_closed_forms_kernel", "kernels_mma_kernel", "kernels_wien_kernel")
+ABI_VERSION = 4
+KERNEL_SPLIT_NAMES = ("pair_closed_forms_kernel", "ic_photon_closed_kernel", "kernels_mma_kernel", "kernels_wien_kernel")
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -92,7 +92,7 @@ def load(variant="product"):
     lib.acro_direct_rates.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.acro_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.acro_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
-    lib.acro_last_kernel_split_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    lib.acro_last_kernel_split_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
     lib.acro_count_work.argtypes = [vp, C.POINTER(Batch), C.POINTER(C.c_int64 * 4), vp]
     lib.acro_launch_count.argtypes = [vp]
     lib.acro_launch_count.restype = i64

@@ -103,7 +103,7 @@ int acro_create(acro_handle_t** out, int device, const acro_tables_t* t, const a
     d.eta = t->eta; d.Yp = t->Y0[1 * 3 + 0]; d.YHe4 = t->Y0[5 * 3 + 0];
     for (int i = 0; i < 27; ++i) d.Y0[i] = t->Y0[i];
     for (int i = 0; i < 5; ++i) cudaEventCreate(&h->ev[i]);
-    cudaEventCreate(&h->lc.split[0]); cudaEventCreate(&h->lc.split[1]);
+    cudaEventCreate(&h->lc.split[0]); cudaEventCreate(&h->lc.split[1]); cudaEventCreate(&h->lc.split[2]);
     *out = h;
     return ACRO_OK;
 }
@@ -114,7 +114,7 @@ int acro_destroy(acro_handle_t* h) {
     cudaFree(h->d_ratedb); cudaFree(h->d_cosmo_lT); cudaFree(h->d_cosmo_ld);
     if (h->host_arena) cudaFree(h->host_arena);
     for (int i = 0; i < 5; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    for (int i = 0; i < 2; ++i) if (h->lc.split[i]) cudaEventDestroy(h->lc.split[i]);
+    for (int i = 0; i < 3; ++i) if (h->lc.split[i]) cudaEventDestroy(h->lc.split[i]);
     delete h;
     return ACRO_OK;
 }
@@ -220,13 +220,14 @@ int acro_last_stage_ms(acro_handle_t* h, float ms[4]) {
     return ACRO_OK;
 }
 
-int acro_last_kernel_split_ms(acro_handle_t* h, float ms[3]) {
+int acro_last_kernel_split_ms(acro_handle_t* h, float ms[4]) {
     if (!h || !ms) return ACRO_EINVAL;
     if (!h->ev_valid || !h->lc.split_valid) return fail(h, ACRO_EINVAL, "the production kernel builder has not run on this handle");
     CU(h, cudaEventSynchronize(h->ev[2]));
     CU(h, cudaEventElapsedTime(&ms[0], h->ev[1], h->lc.split[0]));
     CU(h, cudaEventElapsedTime(&ms[1], h->lc.split[0], h->lc.split[1]));
-    CU(h, cudaEventElapsedTime(&ms[2], h->lc.split[1], h->ev[2]));
+    CU(h, cudaEventElapsedTime(&ms[2], h->lc.split[1], h->lc.split[2]));
+    CU(h, cudaEventElapsedTime(&ms[3], h->lc.split[2], h->ev[2]));
     return ACRO_OK;
 }
 

@@ -30,7 +30,7 @@ struct DirectRateItem {
 
 struct LaunchCounters {
     int64_t launches = 0;
-    cudaEvent_t split[2] = {nullptr, nullptr};   // recorded between the three launches of the production kernel builder
+    cudaEvent_t split[3] = {nullptr, nullptr, nullptr};   // recorded between the launch groups of the production kernel builder
     bool split_valid = false;
 };
 

@@ -47,6 +47,7 @@ __host__ __device__ constexpr int gl_offset(int order) {
 #include "acro_fastquad.cuh"
 #include "acro_tshared.cuh"
 #include "acro_tmma.cuh"
+#include "acro_icphoton.cuh"
 namespace acro {
 
 static void gauss_laguerre(int n, double* x, double* w) {   // alpha = 0; Newton on L_n with the classic initial guesses
@@ -1344,7 +1345,6 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
         // function attributes are per device (each primary context has its own CUfunction): set before every launch
         cudaError_t e = cudaSuccess;
         // function attributes are per device (each primary context has its own CUfunction): set before every launch
-        if ((e = cudaFuncSetAttribute(kernels_mma_kernel<KIND_IC_PHOTON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(kernels_mma_kernel<KIND_IC_ELECTRON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(kernels_mma_kernel<KIND_PC_ELECTRON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         dim3 gp((unsigned)((tri_max + 127) / 128), (unsigned)b.n_points);
@@ -1352,21 +1352,19 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
         lc.launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (lc.split[0]) cudaEventRecord(lc.split[0], st);
-        kernels_mma_kernel<KIND_IC_PHOTON><<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p, ppb);
+        // plane 1 (e -> gamma) in closed form, complete; the shared-grid and Wien kernels do the other two integrals
+        ic_photon_closed_kernel<<<dim3((unsigned)((tri_max + kIcpThreads - 1) / kIcpThreads), (unsigned)b.n_points), kIcpThreads, 0, st>>>(b, Kws, p);
+        lc.launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (lc.split[1]) cudaEventRecord(lc.split[1], st);
         kernels_mma_kernel<KIND_IC_ELECTRON><<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p, ppb);
         kernels_mma_kernel<KIND_PC_ELECTRON><<<grid, kMmThreads, smem, st>>>(b, Kws, closed, t, p, ppb);
-        lc.launches += 3;
+        lc.launches += 2;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (lc.split[1]) lc.split_valid = cudaEventRecord(lc.split[1], st) == cudaSuccess;
-#if ACRO_WT_SPLIT
-        kernels_wien_kernel<64, KIND_IC_PHOTON><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
+        if (lc.split[2]) lc.split_valid = cudaEventRecord(lc.split[2], st) == cudaSuccess;
         kernels_wien_kernel<64, KIND_IC_ELECTRON><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
         kernels_wien_kernel<64, KIND_PC_ELECTRON><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
-        lc.launches += 3;
-#else
-        kernels_wien_kernel<64, -1><<<gp, 128, 0, st>>>(b, Kws, closed, t, p);
-        lc.launches++;
-#endif
+        lc.launches += 2;
         return cudaGetLastError();
     }
 #ifdef ACRO_CROSSCHECK

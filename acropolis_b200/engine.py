@@ -389,7 +389,7 @@ class Engine(object):
     def kernel_split_ms(self):
         """Device time [ms] of the kernel builder's launches in the last acro_run_batch, in the order of
         ``kernel_split_names()``."""
-        ms = (C.c_float * 3)()
+        ms = (C.c_float * len(_lib.KERNEL_SPLIT_NAMES))()
         self._check(self.lib.acro_last_kernel_split_ms(self.h, C.byref(ms)), "acro_last_kernel_split_ms")
         return np.array(list(ms), dtype=np.float64)
 

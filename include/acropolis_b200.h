@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ACRO_ABI_VERSION 3
+#define ACRO_ABI_VERSION 4
 
 #define ACRO_NX 3   /* cascade species: photon, electron, positron        (cascade.py:718)        */
 #define ACRO_NY 9   /* nuclides n,p,d,t,He3,He4,Li6,Li7,Be7              (nucl.py:32-42)          */
@@ -204,9 +204,10 @@ int acro_measure_fp64_peak(acro_handle_t* h, double* tflops);
  * ms[0]=rates, ms[1]=kernels, ms[2]=solve+pdi, ms[3]=matrix.  Synchronises on the recorded events.             */
 int acro_last_stage_ms(acro_handle_t* h, float ms[4]);
 
-/* Split of ms[1] for kernel_mode = ACRO_KERNELS_FAST: ms[0] = pair_closed_forms_kernel, ms[1] = kernels_mma_kernel
- * (temperature-shared grid), ms[2] = kernels_wien_kernel (Wien tail). */
-int acro_last_kernel_split_ms(acro_handle_t* h, float ms[3]);
+/* Split of ms[1] for kernel_mode = ACRO_KERNELS_FAST: ms[0] = pair_closed_forms_kernel, ms[1] = ic_photon_closed_kernel
+ * (e -> gamma plane from tabulated one-variable functions), ms[2] = kernels_mma_kernel (temperature-shared grid, e -> e and
+ * gamma -> e integrals), ms[3] = kernels_wien_kernel (their Wien tail). */
+int acro_last_kernel_split_ms(acro_handle_t* h, float ms[4]);
 
 /* Work census of a (device-resident) batch for the roofline's algorithmic-flop figure: out[0] = (system,i,j>=i) pairs,
  * out[1..3] = pairs with a non-empty range for the e->gamma, e->e and gamma->e thermal integrals (the reference's own

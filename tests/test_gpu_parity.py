@@ -316,7 +316,7 @@ def test_wien_from_parameter(gpu_engine):
             gpu_engine.kernels_of(sp, 0)
     K2, _ = gpu_engine.kernels_of(sp, 19)          # default again (a rejected parameter set leaves the old one active)
     ms = gpu_engine.kernel_split_ms()
-    assert ms.shape == (3,) and (ms > 0).all() and len(gpu_engine.kernel_split_names()) == 3
+    assert ms.shape == (4,) and (ms > 0).all() and len(gpu_engine.kernel_split_names()) == 4
     with wien_from(E1):
         K1, _ = gpu_engine.kernels_of(sp, 19)
     assert np.array_equal(K1 != 0, K2 != 0)

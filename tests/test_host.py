@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.acro_abi_version() == 3 == _lib.ABI_VERSION
+    assert lib.acro_abi_version() == 4 == _lib.ABI_VERSION
     p = _lib.Params()
     lib.acro_default_params(p)
     assert (p.quad_order, p.pdi_cell_order, p.Emin, p.approx_zero, p.Ephb_T_max, p.E_EC_max, p.use_db, p.kernel_mode, p.universal) == \
