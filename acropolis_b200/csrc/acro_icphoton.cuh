@@ -42,25 +42,70 @@ __device__ __forceinline__ double icp_poly(const double* __restrict__ row, doubl
     return p;
 }
 
-// interval of the A/B tables that contains u = ln v, and the local variable in [-1, 1]
+// interval of the A/B tables that contains u = ln v, and the local variable in [-1, 1] (selects, no branch)
 __device__ __forceinline__ int icp_locate(double u, double& x) {
     constexpr int n_lo = (int)((ACRO_ICP_U_SPLIT - ACRO_ICP_U_MIN) / ACRO_ICP_W_LO);
-    if (u >= ACRO_ICP_U_SPLIT) {
-        const double t = (u - ACRO_ICP_U_SPLIT) * (1.0 / ACRO_ICP_W_HI);
-        const int k = min((int)t, ACRO_ICP_N_MAIN - n_lo - 1);
-        x = fma(2.0, t - (double)k, -1.0);
-        return n_lo + k;
-    }
-    const double t = (fmax(u, ACRO_ICP_U_MIN) - ACRO_ICP_U_MIN) * (1.0 / ACRO_ICP_W_LO);   // below e^-40 the functions are constant
-    const int k = min((int)t, n_lo - 1);
+    const bool hi = u >= ACRO_ICP_U_SPLIT;
+    const double t = (fmax(u, ACRO_ICP_U_MIN) - (hi ? ACRO_ICP_U_SPLIT : ACRO_ICP_U_MIN)) * (hi ? 1.0 / ACRO_ICP_W_HI : 1.0 / ACRO_ICP_W_LO);
+    const int k = min((int)t, hi ? ACRO_ICP_N_MAIN - n_lo - 1 : n_lo - 1);     // below e^-40 the functions are constant
     x = fma(2.0, t - (double)k, -1.0);
-    return k;
+    return (hi ? n_lo : 0) + k;
 }
 
-__global__ void __launch_bounds__(kIcpThreads) ic_photon_closed_kernel(acro_batch_t b, double* __restrict__ Kws, acro_params_t p) {
+struct IcpPair {     // per-pair constants of ic_photon_closed_kernel
+    double xa, xb0, lnxa, c9, pre;
+};
+
+// The rare (pair, T) combinations: short ranges (quadrature), upper-limit brackets at a kinematic limit (general table
+// look-ups) and upper limits outside the M, N tables (quadrature).  Not inlined: keeps the main loop small.
+__device__ __noinline__ double icp_slow(const IcpPair& q, double T, double v_cut, bool cut_tab, const double* __restrict__ tA,
+                                        const double* __restrict__ tB, const double* __restrict__ tM, const double* __restrict__ tN,
+                                        const double2* __restrict__ lt) {
+    const double x_cut = v_cut * T;
+    const bool capped = x_cut < q.xb0;
+    const double xb = capped ? x_cut : q.xb0;
+    const double iT = frcp(T);
+    const double va = q.xa * iT, vb = capped ? v_cut : xb * iT, S = vb - va;
+    if (S < kIcpShort || (capped ? !cut_tab : vb < kIcpVTailMin)) {
+        PairConst c;
+        c.c9 = q.c9;
+#if ACRO_FQ_LOGTAB
+        c.lt = lt;
+#endif
+        // short ranges under the cut-off sit at v_a > 199: the 8-node rule of the Wien kernel; anything else: generic
+        return q.pre * (capped && va > 54.598150033144236 ? thermal_integral<KIND_IC_PHOTON, 64, true>(c, T, q.xa, xb, q.xb0)
+                                                          : thermal_integral<KIND_IC_PHOTON, 64>(c, T, q.xa, xb));
+    }
+    const double ua = q.lnxa - log(T);
+    double x;
+    const int k = icp_locate(ua, x);
+    const double ea = fexp(-va);
+    double phi0 = icp_poly(tA + k * kIcpRow, x) * ea;
+    double phi1 = icp_poly(tB + k * kIcpRow, x) * ea;
+    const double ub = flog(vb);
+    const double eb = fexp(-vb);
+    double xq;
+    const int kb = icp_locate(ub, xq);
+    const double Bb = icp_poly(tB + kb * kIcpRow, xq) * eb;
+    const double tt = (ub - ACRO_ICP_U_TAIL) * (1.0 / ACRO_ICP_W_HI);
+    const int kt = min((int)tt, ACRO_ICP_N_TAIL - 1);
+    const double xt = fma(2.0, tt - (double)kt, -1.0);
+    const double Mb = icp_poly(tM + kt * kIcpRow, xt) * eb;
+    const double Nb = icp_poly(tN + kt * kIcpRow, xt) * eb;
+    // L(v_b) = -log1p(-e^-v_b), e^-v_b <= e^-e^2 = 6.2e-4: five terms (the sixth is < 2e-17 of the sum)
+    const double Lb = eb * fma(eb, fma(eb, fma(eb, fma(eb, 0.2, 0.25), 1.0 / 3.0), 0.5), 1.0);
+    phi0 -= Bb + vb * Lb + va * (fma(2.0, ua, 1.0) * Lb - 2.0 * fma(va, Mb, Nb));
+    phi1 -= fma(S, Lb, Bb);
+    return q.pre * (T * T * (1.0 / kPi2)) * fma(q.c9, phi1, phi0);
+}
+
+#ifndef ACRO_ICP_MINBLOCKS
+#define ACRO_ICP_MINBLOCKS 3      // measured (ms per 1000-point slice): 1: 6.0, 2: 4.65, 3: 4.45, 4: 5.0, 6: 10.3 (spills)
+#endif
+__global__ void __launch_bounds__(kIcpThreads, ACRO_ICP_MINBLOCKS) ic_photon_closed_kernel(acro_batch_t b, double* __restrict__ Kws, acro_params_t p) {
     __shared__ double sA[ACRO_ICP_N_MAIN * kIcpRow], sB[ACRO_ICP_N_MAIN * kIcpRow];
     __shared__ double sM[ACRO_ICP_N_TAIL * kIcpRow], sN[ACRO_ICP_N_TAIL * kIcpRow];
-    __shared__ double sT[kIcpChunk], sLnT[kIcpChunk], sPre[kIcpChunk];
+    __shared__ double sT[kIcpChunk], sIT[kIcpChunk], sLnT[kIcpChunk], sPre[kIcpChunk];
     __shared__ double sCut[4];                  // at v = Ephb_T_max: B + v L, L, M, N
     __shared__ int64_t sK[kIcpChunk];
 #if ACRO_FQ_LOGTAB
@@ -108,13 +153,43 @@ __global__ void __launch_bounds__(kIcpThreads) ic_photon_closed_kernel(acro_batc
     const double E = eg[i], Ep = eg[j];
     // limits as in pair_limits() (cascade.py:415-427): nothing below the threshold E' >= E + me
     const bool has = !(Ep < E + kMe);
-    const double xa = has ? 0.25 * kMe2 * E / (Ep * Ep - Ep * E) : 1.0;
-    const double xb0 = fmin(E, Ep - kMe2 / (4.0 * Ep));
-    const double lnxa = log(xa);
+    IcpPair q;
+    q.xa = has ? 0.25 * kMe2 * E / (Ep * Ep - Ep * E) : 1.0;
+    q.xb0 = fmin(E, Ep - kMe2 / (4.0 * Ep));
+    q.lnxa = log(q.xa);
     const double r = E / fmax(Ep - E, 1e-300);
-    const double c9 = r * r / (2.0 + 2.0 * r);
-    const double pre = 2.0 * kPi * (kAlpha * kAlpha) / (Ep * Ep);
+    q.c9 = r * r / (2.0 + 2.0 * r);
+    q.pre = 2.0 * kPi * (kAlpha * kAlpha) / (Ep * Ep);
     double* __restrict__ out = Kws + b.n_pairs_total + loc;        // plane 1
+#if ACRO_FQ_LOGTAB
+    const double2* lt = s_lt;
+#else
+    const double2* lt = nullptr;
+#endif
+    // One entry, branch-free (two of them are in flight per trip of the loop below): the closed form with the cut-off bracket
+    // as a select.  Returns true when the combination needs icp_slow() instead; an empty range yields 0.
+    auto entry = [&](int t, double& val) -> bool {
+        const double T = sT[t], iT = sIT[t];
+        const bool capped = v_cut * T < q.xb0;             // the range ends at the thermal cut-off
+        const double xb = capped ? v_cut * T : q.xb0;
+        const bool live = has && xb > q.xa;
+        const double va = q.xa * iT, vb = capped ? v_cut : xb * iT, S = vb - va;
+        const bool tail = S < kIcpTailFrom;
+        const double ua = q.lnxa - sLnT[t];
+        double x;
+        const int k = icp_locate(ua, x) * kIcpRow;
+        const double ea = fexp(-fmin(va, 700.0));
+        double pa = sA[k + ACRO_ICP_DEG], pb = sB[k + ACRO_ICP_DEG];
+#pragma unroll
+        for (int j = ACRO_ICP_DEG - 1; j >= 0; --j) { pa = fma(pa, x, sA[k + j]); pb = fma(pb, x, sB[k + j]); }
+        const double Lb = sCut[1];
+        const double br0 = sCut[0] + va * (fma(2.0, ua, 1.0) * Lb - 2.0 * fma(va, sCut[2], sCut[3]));
+        const double br1 = fma(-va, Lb, sCut[0]);
+        const bool cut = tail && capped;
+        const double phi0 = fma(pa, ea, cut ? -br0 : 0.0), phi1 = fma(pb, ea, cut ? -br1 : 0.0);
+        val = live ? q.pre * sPre[t] * fma(q.c9, phi1, phi0) : 0.0;
+        return live && (S < kIcpShort || (tail && !(capped && cut_tab)));
+    };
 
     for (int t0 = 0; t0 < nt; t0 += kIcpChunk) {
         const int n = min(kIcpChunk, nt - t0);
@@ -123,63 +198,27 @@ __global__ void __launch_bounds__(kIcpThreads) ic_photon_closed_kernel(acro_batc
             const int s = s0 + t0 + threadIdx.x;
             const double T = b.sys_T[s];
             sT[threadIdx.x] = T;
+            sIT[threadIdx.x] = 1.0 / T;
             sLnT[threadIdx.x] = log(T);
             sPre[threadIdx.x] = T * T * (1.0 / kPi2);
             sK[threadIdx.x] = b.sys_k_off[s];
         }
         __syncthreads();
         if (!valid) continue;
+        int t = 0;
 #pragma unroll 1
-        for (int t = 0; t < n; ++t) {
-            const double T = sT[t];
-            const double x_cut = p.Ephb_T_max * T;
-            const bool capped = x_cut < xb0;           // the range ends at the thermal cut-off
-            const double xb = capped ? x_cut : xb0;
-            double val = 0.0;
-            if (has && xb > xa) {
-                const double iT = frcp(T);
-                const double va = xa * iT, vb = capped ? v_cut : xb * iT, S = vb - va;
-                const bool tail = S < kIcpTailFrom;
-                if (S < kIcpShort || (tail && (capped ? !cut_tab : vb < kIcpVTailMin))) {
-                    PairConst c;
-                    c.c9 = c9;
-#if ACRO_FQ_LOGTAB
-                    c.lt = s_lt;
-#endif
-                    // short ranges under the cut-off sit at v_a > 199: the 8-node rule of the Wien kernel; anything else: generic
-                    val = pre * (capped && va > 54.598150033144236 ? thermal_integral<KIND_IC_PHOTON, 64, true>(c, T, xa, xb, xb0)
-                                                                  : thermal_integral<KIND_IC_PHOTON, 64>(c, T, xa, xb));
-                } else {
-                    const double ua = lnxa - sLnT[t];
-                    double x;
-                    const int k = icp_locate(ua, x);
-                    const double ea = fexp(-va);
-                    double phi0 = icp_poly(sA + k * kIcpRow, x) * ea;
-                    double phi1 = icp_poly(sB + k * kIcpRow, x) * ea;
-                    if (tail && capped) {
-                        const double Lb = sCut[1];
-                        phi0 -= sCut[0] + va * (fma(2.0, ua, 1.0) * Lb - 2.0 * fma(va, sCut[2], sCut[3]));
-                        phi1 -= fma(-va, Lb, sCut[0]);
-                    } else if (tail) {
-                        const double ub = flog(vb);
-                        const double eb = fexp(-vb);
-                        double xq;
-                        const int kb = icp_locate(ub, xq);
-                        const double Bb = icp_poly(sB + kb * kIcpRow, xq) * eb;
-                        const double tt = (ub - ACRO_ICP_U_TAIL) * (1.0 / ACRO_ICP_W_HI);
-                        const int kt = min((int)tt, ACRO_ICP_N_TAIL - 1);
-                        const double xt = fma(2.0, tt - (double)kt, -1.0);
-                        const double Mb = icp_poly(sM + kt * kIcpRow, xt) * eb;
-                        const double Nb = icp_poly(sN + kt * kIcpRow, xt) * eb;
-                        // L(v_b) = -log1p(-e^-v_b), e^-v_b <= e^-e^2 = 6.2e-4: five terms (the sixth is < 2e-17 of the sum)
-                        const double Lb = eb * fma(eb, fma(eb, fma(eb, fma(eb, 0.2, 0.25), 1.0 / 3.0), 0.5), 1.0);
-                        phi0 -= Bb + vb * Lb + va * (fma(2.0, ua, 1.0) * Lb - 2.0 * fma(va, Mb, Nb));
-                        phi1 -= fma(S, Lb, Bb);
-                    }
-                    val = pre * sPre[t] * fma(c9, phi1, phi0);
-                }
-            }
-            out[sK[t]] = val;
+        for (; t + 1 < n; t += 2) {
+            double v0, v1;
+            const bool s0f = entry(t, v0), s1f = entry(t + 1, v1);
+            if (s0f) v0 = icp_slow(q, sT[t], v_cut, cut_tab, sA, sB, sM, sN, lt);
+            if (s1f) v1 = icp_slow(q, sT[t + 1], v_cut, cut_tab, sA, sB, sM, sN, lt);
+            out[sK[t]] = v0;
+            out[sK[t + 1]] = v1;
+        }
+        if (t < n) {
+            double v0;
+            if (entry(t, v0)) v0 = icp_slow(q, sT[t], v_cut, cut_tab, sA, sB, sM, sN, lt);
+            out[sK[t]] = v0;
         }
     }
 }
