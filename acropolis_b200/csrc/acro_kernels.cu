@@ -683,6 +683,12 @@ __global__ void __launch_bounds__(128) pdi_sigma_kernel(acro_batch_t b, double* 
     const int pt = blockIdx.y;
     const int ne = b.pt_ne[pt];
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == ne - 1) {
+        // the column of the last grid point is not a cell: its k = 0 slots carry sigma_r(E0) for the delta-source term of the
+        // rates (nucl.py:441) -- once per point instead of 17 serial evaluations by one lane of every system's warp
+        const double E0 = b.pt_e0[pt], lnE0 = log(E0);
+        for (int r = 0; r < ACRO_NR; ++r) sig[(int64_t)r * b.n_energy_total + b.pt_e_off[pt] + c] = sigma_rt(r, E0, lnE0);
+    }
     if (c >= ne - 1) return;
     const double* E = b.e_grid + b.pt_e_off[pt];
     const double y0 = log(E[c]), y1 = log(E[c + 1]);
@@ -905,9 +911,16 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
             }
         }
     }
-    // (B) the threshold cell of each reaction: lane r integrates [log Eth_r, min(cell end, log Emax)] with
-    //     y = lo + (hi-lo) u^2, which regularises the (E-Q)^p onset of the cross-sections.
-    double thr = 0.0;
+    // (B) the threshold cell of each reaction, [log Eth_r, min(cell end, log Emax)], with y = lo + (hi-lo) u^2, which
+    //     regularises the (E-Q)^p onset of the cross-sections, and
+    // (C) reaction 15 (Be7+a>He3+He4): its closing polynomial changes sign at E = kKink15, where the reference clamps the
+    //     cross-section to zero (nucl.py:327-335) -- a kink inside one grid cell; that cell is integrated only up to the kink
+    //     (the part above it is identically zero) so that no rule straddles it.
+    // Lane r < 17 sets up segment r (B), lane 17 the kink segment (C); their 16-node rules are then dealt to all lanes as
+    // (segment, node) items: two reactions per batch of 32 instead of 17 lanes each running its own cross-section formula
+    // one after the other (that was 0.6 of this kernel's 6.6 ms per benchmark slice).
+    double seg_lo = 0.0, seg_hi = 0.0, seg_ms = 0.0, seg_bs = 0.0;
+    bool seg_on = false;
     if (lane < ACRO_NR) {
         const double Eth = kEth[lane];
         if (Emax > Eth && Eth > E[0]) {
@@ -920,22 +933,12 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
             const double y0 = lnE[c], y1 = lnE[c + 1];
             const double hi = fmin(y1, lnEmax);
             if (hi > lo) {
-                const double ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
-                const double bs = lnF[c + 1] - ms * y1;
-                const double* tx = c_glx + gl_offset(16);
-                const double* tw = c_glw + gl_offset(16);
-                for (int k = 0; k < 16; ++k) {
-                    const double u  = 0.5 * (1.0 + tx[k]);
-                    const double y  = fma(hi - lo, u * u, lo);
-                    const double Ev = exp(y);
-                    thr = fma(tw[k] * 0.5 * (hi - lo) * 2.0 * u * exp(fma(ms, y, bs)) * Ev, sigma_rt(lane, Ev, y), thr);
-                }
+                seg_ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
+                seg_bs = lnF[c + 1] - seg_ms * y1;
+                seg_lo = lo; seg_hi = hi; seg_on = true;
             }
         }
     }
-    // (C) reaction 15 (Be7+a>He3+He4): its closing polynomial changes sign at E = kKink15, where the reference clamps the
-    //     cross-section to zero (nucl.py:327-335) -- a kink inside one grid cell.  Lane 17 integrates that cell only up
-    //     to the kink (the part above it is identically zero) so that no rule straddles it.
     if (lane == ACRO_NR && E[0] < kKink15 && kKink15 < E[top]) {
         int c = (int)((log(kKink15) - lnE[0]) * (double)(ne - 1) / (lnE[ne - 1] - lnE[0]));
         c = max(0, min(c, ne - 2));
@@ -945,31 +948,54 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
             const double y0 = lnE[c], y1 = lnE[c + 1];
             const double hi = fmin(fmin(y1, lnEmax), log(kKink15));
             if (hi > y0) {
-                const double ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
-                const double bs = lnF[c + 1] - ms * y1;
-                const double* tx = c_glx + gl_offset(16);
-                const double* tw = c_glw + gl_offset(16);
-                const double h = 0.5 * (hi - y0), m = 0.5 * (hi + y0);
-                for (int k = 0; k < 16; ++k) {
-                    const double y  = fma(h, tx[k], m);
-                    const double Ev = exp(y);
-                    thr = fma(tw[k] * h * exp(fma(ms + 1.0, y, bs)), sigma_rt(14, Ev, y), thr);
+                seg_ms = (lnF[c + 1] - lnF[c]) / (y1 - y0);
+                seg_bs = lnF[c + 1] - seg_ms * y1;
+                seg_lo = y0; seg_hi = hi; seg_on = true;
+            }
+        }
+    }
+    {
+        const unsigned segs = __ballot_sync(0xffffffffu, seg_on);
+        const int n_items = __popc(segs) * 16;
+        const double* tx = c_glx + gl_offset(16);
+        const double* tw = c_glw + gl_offset(16);
+        for (int base = 0; base < n_items; base += 32) {
+            const int it = base + lane;
+            const bool live = it < n_items;
+            const int src = live ? __fns(segs, 0, (it >> 4) + 1) : 0;
+            const double lo = __shfl_sync(0xffffffffu, seg_lo, src), hi = __shfl_sync(0xffffffffu, seg_hi, src);
+            const double ms = __shfl_sync(0xffffffffu, seg_ms, src), bs = __shfl_sync(0xffffffffu, seg_bs, src);
+            if (live) {
+                const int k = it & 15;
+                const int r = src < ACRO_NR ? src : 14;
+                double y, wgt;
+                if (src < ACRO_NR) {
+                    const double u = 0.5 * (1.0 + tx[k]);
+                    y = fma(hi - lo, u * u, lo);
+                    wgt = tw[k] * 0.5 * (hi - lo) * 2.0 * u;
+                } else {
+                    const double h = 0.5 * (hi - lo);
+                    y = fma(h, tx[k], 0.5 * (hi + lo));
+                    wgt = tw[k] * h;
                 }
+                const double Ev = exp(y);
+                accs[r * 32 + lane] = fma(wgt * exp(fma(ms, y, bs)) * Ev, sigma_rt(r, Ev, y), accs[r * 32 + lane]);
             }
         }
     }
     const double rate_E0 = g[top];   // Gamma_gamma(E0, T): the grid's last point is E0 (cascade.py:745, nucl.py:436)
     const double lnE0 = log(E0);
-#pragma unroll 1
-    for (int r = 0; r < ACRO_NR; ++r) {
-        double v = warp_sum(accs[r * 32 + lane]);
-        v += __shfl_sync(0xffffffffu, thr, r);
-        if (r == 14) v += __shfl_sync(0xffffffffu, thr, ACRO_NR);
-        if (lane == 0) {
-            double rate = S0[0] * kMbToIMeV2 * sigma_rt(r, E0, lnE0) / rate_E0;
-            if (Emax > kEth[r]) rate += kMbToIMeV2 * v;
-            pdi[(int64_t)s * ACRO_NR + r] = fmax(p.approx_zero, rate);
-        }
+    __syncwarp();
+    if (lane < ACRO_NR) {
+        // lane r adds up the 32 per-lane partial sums of reaction r (columns visited in a rotated order: no bank conflicts)
+        const int r = lane;
+        double v = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) v += accs[r * 32 + ((j + r) & 31)];
+        const double sig0 = sig ? sig[(int64_t)r * b.n_energy_total + b.pt_e_off[pt] + top] : sigma_rt(r, E0, lnE0);
+        double rate = S0[0] * kMbToIMeV2 * sig0 / rate_E0;
+        if (Emax > kEth[r]) rate += kMbToIMeV2 * v;
+        pdi[(int64_t)s * ACRO_NR + r] = fmax(p.approx_zero, rate);
     }
 }
 
@@ -1412,7 +1438,7 @@ cudaError_t launch_solve_pdi(const acro_batch_t& b, const acro_out_t& o, const D
     }
     const int blocks = (b.n_systems + wpb - 1) / wpb;
     if (sig && o.pdi && b.ne_max > 1) {
-        dim3 gs((unsigned)((b.ne_max - 1 + 127) / 128), (unsigned)b.n_points);
+        dim3 gs((unsigned)((b.ne_max + 127) / 128), (unsigned)b.n_points);
         pdi_sigma_kernel<<<gs, 128, 0, st>>>(b, sig, p);
         lc.launches++;
         cudaError_t e = cudaGetLastError();
