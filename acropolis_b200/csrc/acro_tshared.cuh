@@ -154,12 +154,13 @@ constexpr int kWienChunk = 64;   // temperatures pooled per pass
 // neighbouring pairs with similar x_a/T, hence the same Gauss-Laguerre order and coalesced stores; pooling consecutive
 // temperatures fills the lanes that would idle.  (Pair-major pooling was measured 25 % SLOWER than no pooling: every
 // batch of 32 items then spans the whole x_a/T range of a pair and runs at the largest node count.)
-//   smask[t]  = ballot of the lanes whose range contains temperature c_lo + t,  spref[t] = exclusive prefix of popc
+//   smask[t]  = ballot of the lanes whose range contains temperature c_lo + t;  slist = the chunk's items in that order
 template <int KIND, int Q>
 __device__ __forceinline__ void wien_pooled(const acro_batch_t& b, double* __restrict__ Kws, const acro_params_t& p, int s0, int nt,
                                             int t_lo, int n_mine, double x_a, double x_b0, double c0, double c1, double c2,
                                             double c3, double pre, long long loc, int lane, unsigned* __restrict__ smask,
-                                            int* __restrict__ spref, const double2* __restrict__ lt, const DeviceTables& tb) {
+                                            unsigned short* __restrict__ slist,
+                                            const double2* __restrict__ lt, const DeviceTables& tb) {
     const int64_t np = b.n_pairs_total;
     const int t_hi = t_lo + n_mine;
     int w_lo = n_mine > 0 ? t_lo : nt, w_hi = n_mine > 0 ? t_hi : 0;
@@ -214,22 +215,23 @@ __device__ __forceinline__ void wien_pooled(const acro_batch_t& b, double* __res
         }
         const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
         const int total = tot0 + __shfl_sync(0xffffffffu, inc1, 31);
-        spref[lane] = inc0 - cnt0;
-        spref[32 + lane] = tot0 + inc1 - cnt1;
+        // item list of the chunk, temperature-major: (slot << 5) | owning lane.  Lane l expands the masks of slots l and 32 + l;
+        // a batch then reads its 32 items with one load each (a binary search over the prefix plus __fns per item was 25 %
+        // of this kernel's instructions)
+        {
+            int pos = inc0 - cnt0;
+            unsigned m = (lane < nc) ? smask[lane] : 0u;
+            while (m) { slist[pos++] = (unsigned short)((lane << 5) | (__ffs(m) - 1)); m &= m - 1; }
+            pos = tot0 + inc1 - cnt1;
+            m = (32 + lane < nc) ? smask[32 + lane] : 0u;
+            while (m) { slist[pos++] = (unsigned short)(((32 + lane) << 5) | (__ffs(m) - 1)); m &= m - 1; }
+        }
         __syncwarp();
         for (int base = 0; base < total; base += 32) {
             const int q = base + lane;
             const bool live = q < total;
-            int tt = 0, own = 0;
-            if (live) {
-                int lo = 0, hi = nc - 1;          // last temperature slot whose exclusive prefix is <= q and that is non-empty
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (spref[mid] <= q) lo = mid; else hi = mid - 1;
-                }
-                tt = lo;
-                own = __fns(smask[tt], 0, q - spref[tt] + 1);   // the (q - prefix + 1)-th set bit
-            }
+            const int item = live ? slist[q] : 0;
+            const int tt = item >> 5, own = item & 31;
             const double o_xa = shfl_d(x_a, own), o_xb0 = shfl_d(x_b0, own), o_pre = shfl_d(pre, own);
             const double o_c0 = shfl_d(c0, own), o_c1 = shfl_d(c1, own), o_c2 = shfl_d(c2, own), o_c3 = shfl_d(c3, own);
             const long long o_loc = __shfl_sync(0xffffffffu, loc, own);
@@ -276,10 +278,10 @@ __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(ac
     const int ne = b.pt_ne[pt], nt = b.pt_nt[pt], s0 = b.pt_sys_off[pt];
     const int64_t tri = (int64_t)ne * (ne + 1) / 2;
     __shared__ unsigned smask_all[4 * kWienChunk];
-    __shared__ int spref_all[4 * kWienChunk];
+    __shared__ unsigned short slist_all[4 * kWienChunk * 32];
     const int lane = threadIdx.x & 31;
     unsigned* smask = smask_all + (threadIdx.x >> 5) * kWienChunk;
-    int* spref = spref_all + (threadIdx.x >> 5) * kWienChunk;
+    unsigned short* slist = slist_all + (threadIdx.x >> 5) * kWienChunk * 32;
     const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 #if ACRO_FQ_LOGTAB
     __shared__ double2 s_lt[kLogTab];
@@ -324,18 +326,18 @@ __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(ac
     if (KSEL < 0 || KSEL == KIND_IC_PHOTON) {   // e -> gamma
         range(L.xa9, L.xb9, L.xa9 > 0.0, 0, t_lo, n);
         const double r = E / fmax(Ep - E, 1e-300);
-        wien_pooled<KIND_IC_PHOTON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa9, L.xb9, r * r / (2.0 + 2.0 * r), 0.0, 0.0, 0.0, pre_ic, loc, lane, smask, spref, lt, tb);
+        wien_pooled<KIND_IC_PHOTON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa9, L.xb9, r * r / (2.0 + 2.0 * r), 0.0, 0.0, 0.0, pre_ic, loc, lane, smask, slist, lt, tb);
     }
     if (KSEL < 0 || KSEL == KIND_IC_ELECTRON) {   // e -> e
         range(L.xa10, L.xb10, L.xa10 > 0.0, 0, t_lo, n);
-        wien_pooled<KIND_IC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa10, L.xb10, E, Ep - E, 0.25 * kMe2 / Ep, 0.5 / Ep, pre_ic, loc, lane, smask, spref, lt, tb);
+        wien_pooled<KIND_IC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa10, L.xb10, E, Ep - E, 0.25 * kMe2 / Ep, 0.5 / Ep, pre_ic, loc, lane, smask, slist, lt, tb);
     }
     if (KSEL < 0 || KSEL == KIND_PC_ELECTRON) {   // gamma -> e (pair creation): needs E' >= me^2/(50 T)
         const int t_pc = first_true(Tg, nt, [&](double T) { return !(Ep < kMe2 / (50.0 * T)); });
         range(L.xa11, L.xb11, true, t_pc, t_lo, n);
         const int64_t oc = b.pt_pair_off[pt] + locc;
         wien_pooled<KIND_PC_ELECTRON, Q>(b, Kws, p, s0, nt, t_lo, n, L.xa11, L.xb11, E, Ep, closed[2 * b.n_pairs_points + oc],
-                                         closed[b.n_pairs_points + oc], pre_pc, loc, lane, smask, spref, lt, tb);
+                                         closed[b.n_pairs_points + oc], pre_pc, loc, lane, smask, slist, lt, tb);
     }
 }
 
