@@ -34,9 +34,10 @@ namespace acro {
 
 // Gauss-Laguerre rules n = 4, 6, 8, 12, 16, 24 packed back to back (offsets 0, 4, 10, 18, 30, 46): nodes, weights
 // (include e^{-s}), e^{-s_k}
-__constant__ double c_lag_s[70];
-__constant__ double c_lag_w[70];
-__constant__ double c_lag_es[70];
+constexpr int kLagTotal = 80;     // Gauss-Laguerre rules of order 4, 6, 8, 12, 16, 24, 10 back to back
+__constant__ double c_lag_s[kLagTotal];
+__constant__ double c_lag_w[kLagTotal];
+__constant__ double c_lag_es[kLagTotal];
 
 #ifndef ACRO_FQ_LAG_UNROLL
 #define ACRO_FQ_LAG_UNROLL 2
@@ -221,14 +222,14 @@ __device__ __forceinline__ double thermal_integral(const PairConst& c, double T,
     const double va = x_a * iT;
     if ((STEEP_ONLY || va > kSteepX) && (x_b - x_a) * iT >= kSteepSpan) {
         // Gauss-Laguerre in s = (x - x_a)/T.  The further out on the Wien tail, the smoother the integrand on the scale of
-        // the weight, so the order follows va = x_a/T (worst relative error of each band in tools/proto, all <= 4e-10):
-        //   va in (e, e^1.5]: 24   (e^1.5, e^2]: 16   (e^2, e^2.5]: 12   (e^2.5, e^3]: 8   (e^3, e^4]: 6   > e^4: 4
+        // the weight, so the order follows va = x_a/T (worst relative error of each band in tools/proto/wien_orders.py, all
+        // <= 4e-10):   va in (e, e^1.5]: 24   (e^1.5, e^2]: 16   (e^2, e^2.5]: 10   (e^2.5, e^3]: 8   (e^3, e^4]: 6   > e^4: 4
         const double Ea = fexp(-va);
         int n, off;
         if (va > 54.598150033144236) { n = 4; off = 0; }
         else if (va > 20.085536923187668) { n = 6; off = 4; }
         else if (va > 12.182493960703473) { n = 8; off = 10; }
-        else if (va > 7.38905609893065) { n = 12; off = 18; }
+        else if (va > 7.38905609893065) { n = 10; off = 70; }
         else if (va > 4.4816890703380645) { n = 16; off = 30; }
         else { n = 24; off = 46; }
         double sum = 0.0;

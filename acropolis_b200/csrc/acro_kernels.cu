@@ -102,13 +102,13 @@ cudaError_t upload_quadrature_tables() {
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_glw, w.data(), sizeof(double) * kGLTotal);
     if (e != cudaSuccess) return e;
-    double ls[70], lw[70], les[70];
+    double ls[kLagTotal], lw[kLagTotal], les[kLagTotal];
     {
-        const int orders_l[6] = {4, 6, 8, 12, 16, 24};
+        const int orders_l[7] = {4, 6, 8, 12, 16, 24, 10};    // offsets 0, 4, 10, 18, 30, 46, 70 (thermal_integral)
         int off = 0;
         for (int o : orders_l) { gauss_laguerre(o, ls + off, lw + off); off += o; }
     }
-    for (int i = 0; i < 70; ++i) les[i] = std::exp(-ls[i]);
+    for (int i = 0; i < kLagTotal; ++i) les[i] = std::exp(-ls[i]);
     if ((e = cudaMemcpyToSymbol(c_lag_s, ls, sizeof(ls))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_lag_w, lw, sizeof(lw))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_lag_es, les, sizeof(les))) != cudaSuccess) return e;
