@@ -1364,7 +1364,8 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
                                               2 * kLogTab + kPanN * kPanN + (size_t)kMmWarps * MM_NCONST * 32);
         const int64_t passes_max = (tri_max + kMmPairs - 1) / kMmPairs;
         // passes (32 pairs per warp) per block and Bose-table fill: up to kMmPassesPerBlock for scan batches (measured, 512
-        // threads, ms per 1000-point slice: 1: 28.5, 2: 24.8, 4: 22.9, 8: 19.8, 12: 19.6), fewer while that would leave less
+        // threads, ms per 1000-point slice with three integrals: 1: 28.5, 2: 24.8, 4: 22.9, 8: 19.8, 12: 19.6; with two: 8: 13.6, 12: 13.5,
+        // 16: 13.4, 24: 13.1, 32: 12.8, 48: 12.7 -- a block drains once, when its slowest warp is done), fewer while that would leave less
         // than two blocks per SM (single points and short batches: latency, not throughput)
         const int ppb = (int)std::max<int64_t>(1, std::min<int64_t>(kMmPassesPerBlock, (int64_t)b.n_points * passes_max / (2 * (int64_t)sm_count())));
         dim3 grid((unsigned)((passes_max + ppb - 1) / ppb), (unsigned)b.n_points);

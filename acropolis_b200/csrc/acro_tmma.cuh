@@ -36,7 +36,7 @@ constexpr int kMmThreads = ACRO_MM_THREADS;
 constexpr int kMmWarps = kMmThreads / 32;
 constexpr int kMmPairs = kMmWarps * 32;       // pairs per macro-pass of a block (32 per warp: phase A has lane = pair)
 #ifndef ACRO_MM_PASSES
-#define ACRO_MM_PASSES 12                     // macro-passes (32 pairs per warp each) per block and Bose-table fill
+#define ACRO_MM_PASSES 48                     // macro-passes (32 pairs per warp each) per block and Bose-table fill
 #endif
 constexpr int kMmPassesPerBlock = ACRO_MM_PASSES;
 constexpr int kMmNT = kTT / 8;                // N-tiles (8 temperatures each)

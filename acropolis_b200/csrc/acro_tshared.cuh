@@ -132,7 +132,7 @@ __device__ __forceinline__ int panel_of(const SharedGrid& g, double y) {   // pa
 // pools its items: exclusive prefix sum of the range lengths, then 32 items at a time, each lane fetching the constants
 // of the owning pair with shuffles.
 #ifndef ACRO_WT_MINBLOCKS
-#define ACRO_WT_MINBLOCKS 10
+#define ACRO_WT_MINBLOCKS 8
 #endif
 
 // first index t in [0, nt) with pred(T[t]) true, for a predicate that is false...false true...true along the grid

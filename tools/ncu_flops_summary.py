@@ -9,7 +9,7 @@ smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_execu
 sm__inst_executed_pipe_tensor_subpipe_dmma.sum,sm__inst_executed_pipe_fp64.sum,\
 sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active,\
 dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-        -k regex:"pair_closed|kernels_mma|kernels_wien|solve_pdi" -c 16 --csv --log-file gpurun_out/r02_flops.csv \
+        -k regex:"pair_closed|ic_photon|kernels_mma|kernels_wien|solve_pdi" -c 28 --csv --log-file gpurun_out/r02_flops.csv \
         python bench.py --steps 1 --warmup 3 --no-cpu
 
 Here:   python tools/ncu_flops_summary.py gpurun_out/r02_flops.csv
@@ -27,8 +27,8 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SHORT = ("pair_closed_forms_kernel", "kernels_mma_kernel", "kernels_wien_kernel", "solve_pdi_kernel", "kernels_shared4_kernel",
-         "direct_rates_kernel")
+SHORT = ("pair_closed_forms_kernel", "ic_photon_closed_kernel", "kernels_mma_kernel", "kernels_wien_kernel", "solve_pdi_kernel",
+         "kernels_shared4_kernel", "direct_rates_kernel")
 
 
 def source_hash():
@@ -67,7 +67,8 @@ def main(path, out_path):
         if short is None:
             continue
         launches.setdefault(short, {}).setdefault(int(r[ix["ID"]]), {})[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
-    n_slices = len(launches.get("kernels_mma_kernel") or max(launches.values(), key=len))
+    # one pair_closed_forms_kernel launch per slice; kernels_mma_kernel / kernels_wien_kernel launch once per integral kind
+    n_slices = len(launches.get("pair_closed_forms_kernel") or min(launches.values(), key=len))
     trip = slice_triples(n_slices)
     kernels = {}
     for short, byid in launches.items():
