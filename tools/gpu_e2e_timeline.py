@@ -20,8 +20,8 @@ def launch(self, ch, stages=7 | 8):
     evs.append((a, b, ch["cnt"]["n_points"], time.perf_counter()))
 Engine.launch = launch
 import itertools
-CFG = [(64, 64)]
-for (fg, gr), rep in itertools.product(CFG, range(8)):
+CFG = [(fg, 64) for fg in (32, 48, 64, 96, 128, 192)]
+for (fg, gr), rep in itertools.product(CFG, range(4)):
     par = slice_params(pts, rep)
     torch.cuda.synchronize()
     del evs[:]
@@ -30,7 +30,7 @@ for (fg, gr), rep in itertools.product(CFG, range(8)):
     rows = run_points(model, par, devices=[0], first_group=fg, growth=gr)
     t1 = time.perf_counter()
     torch.cuda.synchronize()
-    if rep >= 1:
+    if rep >= 2:
         print("first_group %d growth %d:" % (fg, gr), "call %.1f ms wall; groups (points, host launch time since start [ms], GPU ms, idle gap before [ms]):" % (1e3 * (t1 - t0)))
         prev = None
         for a, b, n, th in evs:
