@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
         (64, 8, 1.5, 1e-200, 200.0, 10.0, 1, 0, 0)
     # the test build (cross-check kernel modes) exports the same ABI
     x = _lib.load("xcheck")
-    assert x.acro_abi_version() == 3 and all(getattr(x, n) is not None for n in declared)
+    assert x.acro_abi_version() == _lib.ABI_VERSION and all(getattr(x, n) is not None for n in declared)
 
 
 def test_product_library_ships_without_crosscheck_kernels():
