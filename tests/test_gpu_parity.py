@@ -382,3 +382,36 @@ def test_pdi_rates_vs_converged_reference_integrand(results, name):
     ex = golden("pdi_exact.npz")[name + "_pdi_exact"]
     assert relerr(r["pdi"], ex, 1e-100) < 1e-6
     assert relerr(z["pdi"], ex, 1e-100) > 2e-6           # the tight reference itself is further away than that
+
+
+@pytest.mark.gpu
+def test_closed_form_photon_plane_corners(gpu_engine, xcheck_engine):
+    """ic_photon_closed_kernel (e -> gamma plane from tabulated one-variable functions) in the corners of its case analysis,
+    against the plain Gauss-Legendre evaluation of the same integral (cross-check build, Q = 96, reference F and range tests).
+    Temperatures are placed relative to one pair's lower limit x_a so that the row hits: v_a just below the thermal cut-off
+    (range shorter than 1/4: 8-node rule; between 1/4 and 36: bracket from the per-block constants), the Wien tail without a
+    bracket, the shared-grid range, and temperatures so hot that the range ends at the KINEMATIC limit with a bracket that
+    matters (general table look-ups) or below the M, N tables (v_b < e^2: quadrature)."""
+    import acropolis_b200.params as params
+    from acropolis_b200.engine import PointSpec, energy_grid
+    E0 = 60.0
+    Eg = energy_grid(E0)
+    i, j = 5, len(Eg) - 20
+    E, Ep = Eg[i], Eg[j]
+    me2 = params.me2
+    xa = 0.25 * me2 * E / (Ep * Ep - Ep * E)
+    va = np.array([199.95, 199.8, 199.0, 190.0, 170.0, 120.0, 40.0, 9.0, 5.0, 0.5, 1e-2])
+    T = np.sort(np.concatenate([xa / va, [Eg[0] / 30.0, Eg[0] / 10.0, Eg[0] / 6.0, Eg[0] / 3.0]]))
+    sp = PointSpec(E0, Eg, T, np.ones((len(T), 3)), 0.0)
+    worst = 0.0
+    for it in range(len(T)):
+        try:
+            params.kernel_mode, params.quad_order = 1, 96
+            Kp, _ = xcheck_engine.kernels_of(sp, it)
+        finally:
+            params.kernel_mode, params.quad_order = 0, 64
+        Kf, _ = gpu_engine.kernels_of(sp, it)
+        assert np.array_equal(Kf[1] != 0, Kp[1] != 0), it
+        worst = max(worst, relerr(Kf[1], Kp[1]))
+        assert Kf[1][i, j] > 0
+    assert worst < 2e-8, worst

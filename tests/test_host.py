@@ -471,3 +471,31 @@ def test_scan_deviations_grid_and_exclusion():
         assert np.all(plots._get_deviations(nod, plots.pdg2022)[2] == 10)
     with pytest.raises(ImportError, match="matplotlib"):
         plots.plot_scan_results(data)
+
+
+def test_icphoton_tables_against_quadrature():
+    """The generated tables of the closed-form e -> gamma kernel (csrc/acro_icphoton_tab.h): the double-precision evaluation
+    that ic_photon_closed_kernel performs (tools/make_icphoton_tables.py::phi_double, same operation order) against adaptive
+    quadrature of the original integrals  int F-part * v/(e^v - 1) dv, in the regimes the kernel uses them: shared-grid range
+    (v_a < e^2), Wien tail, upper-limit bracket at the thermal cut-off, short range."""
+    from scipy.integrate import quad
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_icphoton_tables as g
+    tabs = g.load_header()
+    assert tabs["A"].shape == (43, 12) and tabs["M"].shape == (7, 12)
+
+    def exact(va, vb):
+        h = lambda q: 2 * q * np.log(q) + (1 + 2 * q) * (1 - q)
+        bose = lambda s: 1.0 / (-np.expm1(-(va + s)))
+        S = vb - va
+        brk = [x for x in (0.25, 1.0, 4.0, 12.0, 30.0, 70.0) if x < S]
+        f0 = quad(lambda s: h(va / (va + s)) * (va + s) * np.exp(-s) * bose(s), 0, S, points=brk, epsabs=0, epsrel=1e-13, limit=400)[0]
+        f1 = quad(lambda s: s * np.exp(-s) * bose(s), 0, S, points=brk, epsabs=0, epsrel=1e-13, limit=400)[0]
+        return f0 * np.exp(-va), f1 * np.exp(-va)
+
+    for va, vb in ((1e-7, 200.0), (3e-3, 150.0), (0.4, 30.0), (2.5, 200.0), (7.0, 40.0), (7.0, 200.0), (12.0, 200.0), (60.0, 200.0),
+                   (150.0, 200.0), (180.0, 200.0), (199.0, 200.0), (199.7, 200.0), (5.0, 9.0), (0.05, 8.0)):
+        e0, e1 = exact(va, vb)
+        g0, g1 = g.phi_double(tabs, va, vb)
+        tol = 1e-9 if vb - va < 2 else 1e-11
+        assert abs(g0 / e0 - 1) < tol and abs(g1 / e1 - 1) < tol, (va, vb, g0 / e0 - 1, g1 / e1 - 1)

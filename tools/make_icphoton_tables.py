@@ -201,6 +201,18 @@ def check(tabs, n=500, seed=0):
     return worst
 
 
+def load_header(path=OUT):
+    """The four tables back from the generated header (tests/test_host.py checks them against scipy quadrature)."""
+    import re
+    txt = open(path).read()
+    tabs = {}
+    for name in "ABMN":
+        m = re.search(r"kIcp%s\[(\d+)\]\[(\d+)\] = \{(.*?)\};" % name, txt, re.S)
+        vals = [float(v) for v in re.findall(r"[-+]?\d\.\d+e[-+]\d+", m.group(3))]
+        tabs[name] = np.array(vals).reshape(int(m.group(1)), int(m.group(2)))
+    return tabs
+
+
 def write_header(tabs):
     def arr(name, a):
         rows = ",\n".join("    {" + ", ".join("%.17e" % v for v in r) + "}" for r in a)

@@ -10,7 +10,7 @@ WANT = ("Kernel Name", "Block Size", "Grid Size", "dram__bytes_read.sum", "dram_
         "sm__cycles_elapsed.max", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__maximum_warps_per_active_cycle_pct",
-        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active")
 PREFIX = ("smsp__average_warps_issue_stalled_",)
 ALSO = ("smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -19,9 +19,13 @@ ALSO = ("smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained
 rep, header = sys.argv[1], sys.argv[2:]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-names, units, vals = rows[0], rows[1], rows[2]
+names, units = rows[0], rows[1]
 for h in header:
     print("# " + h)
-for i, n in enumerate(names):
-    if n in WANT or n in ALSO or (n.startswith(PREFIX) and n.endswith("_per_issue_active.ratio")):
-        print("%-88s %-16s %s" % (n, units[i], vals[i]))
+for vals in rows[2:]:          # one block per captured launch
+    if len(vals) != len(names):
+        continue
+    for i, n in enumerate(names):
+        if n in WANT or n in ALSO or (n.startswith(PREFIX) and n.endswith("_per_issue_active.ratio")):
+            print("%-88s %-16s %s" % (n, units[i], vals[i]))
+    print()
