@@ -523,8 +523,9 @@ def gpu_slices(args, w):
                          "algorithmic_tflops": flop_alg / t_kernels / 1e12,
                          "algorithmic_speedup": (flop_alg / (exec_flop_total or np.nan)) if exec_flop_total else None,
                          "algorithmic_note": "SURVEY 8d convention (Q=63 nodes per (E,E',T) integral); the production path executes "
-                                             "fewer operations than that convention counts (F/G once per node for all T; 4-12 "
-                                             "Laguerre nodes on the Wien tail), hence algorithmic_speedup > 1",
+                                             "fewer operations than that convention counts (e->gamma plane from tabulated one-variable "
+                                             "functions, no quadrature; F/G once per grid node for all T; 4-10 Laguerre nodes on the "
+                                             "Wien tail), hence algorithmic_speedup > 1",
                          "census": {"pairs": pairs, "N_a9": n9, "N_a10": n10, "N_a11": n11, "Q": Q,
                                     "fractions": census_fractions(census)}},
             "roofline_solve": {"kernel": "solve_pdi_kernel (stage ii+iii)", "bound": "hbm", "achieved": solve_bytes / t_solve / 1e9,
