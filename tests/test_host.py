@@ -499,3 +499,23 @@ def test_icphoton_tables_against_quadrature():
         g0, g1 = g.phi_double(tabs, va, vb)
         tol = 1e-9 if vb - va < 2 else 1e-11
         assert abs(g0 / e0 - 1) < tol and abs(g1 / e1 - 1) < tol, (va, vb, g0 / e0 - 1, g1 / e1 - 1)
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference needs no GPU (the CPU port of the reference's algorithm on the host cores): one JSON line with
+    the driver's keys, e2e equal to the line's own value with zero transfer bytes, a cpu_baseline that describes the run; under
+    torchrun every rank but 0 exits 0 without a line."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "points/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["metric"].startswith("scan points/sec") and d["config"]["name"] == "cfg3" and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "27" in cb["sample"]
+    env1 = dict(env, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=120, env=env1, cwd=ROOT)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
