@@ -34,6 +34,7 @@ constexpr int kIcpRow = ACRO_ICP_DEG + 1;
 constexpr double kIcpTailFrom = 36.0;         // v_b - v_a from which the upper-limit bracket is dropped
 constexpr double kIcpShort = 0.25;            // v_b - v_a below which the brackets cancel (> 1e3 x rounding): quadrature
 constexpr double kIcpVTailMin = 7.38905609893065;   // e^ACRO_ICP_U_TAIL: M, N are tabulated from here
+constexpr double kIcpVMax = 244.0;                  // < e^ACRO_ICP_U_MAX: end of all tables (only reachable with Ephb_T_max > 244)
 
 __device__ __forceinline__ double icp_poly(const double* __restrict__ row, double x) {
     double p = row[ACRO_ICP_DEG];
@@ -66,7 +67,7 @@ __device__ __noinline__ double icp_slow(const IcpPair& q, double T, double v_cut
     const double xb = capped ? x_cut : q.xb0;
     const double iT = frcp(T);
     const double va = q.xa * iT, vb = capped ? v_cut : xb * iT, S = vb - va;
-    if (S < kIcpShort || (capped ? !cut_tab : vb < kIcpVTailMin)) {
+    if (S < kIcpShort || va > kIcpVMax || vb > kIcpVMax || (S < kIcpTailFrom && (capped ? !cut_tab : vb < kIcpVTailMin))) {
         PairConst c;
         c.c9 = q.c9;
 #if ACRO_FQ_LOGTAB
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kIcpThreads, ACRO_ICP_MINBLOCKS) ic_photon_clo
     }
     __syncthreads();
     const double v_cut = p.Ephb_T_max;
-    const bool cut_tab = v_cut >= kIcpVTailMin && v_cut <= 244.0;      // inside the M, N tables (e^2 .. e^5.5)
+    const bool cut_tab = v_cut >= kIcpVTailMin && v_cut <= kIcpVMax;   // inside the M, N tables (e^2 .. e^5.5)
     if (threadIdx.x == 0 && cut_tab) {
         const double ub = log(v_cut), eb = exp(-v_cut);
         double xq;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kIcpThreads, ACRO_ICP_MINBLOCKS) ic_photon_clo
         const bool cut = tail && capped;
         const double phi0 = fma(pa, ea, cut ? -br0 : 0.0), phi1 = fma(pb, ea, cut ? -br1 : 0.0);
         val = live ? q.pre * sPre[t] * fma(q.c9, phi1, phi0) : 0.0;
-        return live && (S < kIcpShort || (tail && !(capped && cut_tab)));
+        return live && (S < kIcpShort || va > kIcpVMax || (tail && !(capped && cut_tab)));
     };
 
     for (int t0 = 0; t0 < nt; t0 += kIcpChunk) {

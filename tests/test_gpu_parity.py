@@ -415,3 +415,21 @@ def test_closed_form_photon_plane_corners(gpu_engine, xcheck_engine):
         worst = max(worst, relerr(Kf[1], Kp[1]))
         assert Kf[1][i, j] > 0
     assert worst < 2e-8, worst
+    # a thermal cut-off beyond the tables (Ephb_T_max = 300 > e^5.5): entries with v_a or v_b > 244 fall back to quadrature
+    T2 = np.sort(xa / np.array([299.9, 299.0, 280.0, 250.0, 243.0, 230.0, 100.0, 3.0]))
+    sp2 = PointSpec(E0, Eg, T2, np.ones((len(T2), 3)), 0.0)
+    old_cut = params.Ephb_T_max
+    try:
+        params.Ephb_T_max = 300.0
+        for it in range(len(T2)):
+            try:
+                params.kernel_mode, params.quad_order = 1, 96
+                Kp, _ = xcheck_engine.kernels_of(sp2, it)
+            finally:
+                params.kernel_mode, params.quad_order = 0, 64
+            Kf, _ = gpu_engine.kernels_of(sp2, it)
+            assert np.array_equal(Kf[1] != 0, Kp[1] != 0), it
+            assert relerr(Kf[1], Kp[1]) < 2e-8, it
+            assert Kf[1][i, j] > 0
+    finally:
+        params.Ephb_T_max = old_cut
