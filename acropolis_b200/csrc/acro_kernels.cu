@@ -1034,10 +1034,152 @@ __device__ inline void mm9(const double* A, const double* B, double* C) {
         }
 }
 
+// the entry-wise combinations of the Pade-13 numerator/denominator, shared by the serial and the warp-cooperative form so that
+// both round alike (explicit fma: no dependence on what the compiler contracts)
+__device__ __forceinline__ double pade_w1(const double* b, double a2, double a4, double a6, int top) {
+    return fma(b[top - 4], a2, fma(b[top - 2], a4, b[top] * a6));                      // b_top A6 + b_(top-2) A4 + b_(top-4) A2
+}
+__device__ __forceinline__ double pade_w2(const double* b, double v, double a2, double a4, double a6, int top, bool diag) {
+    return fma(b[top - 4], a2, fma(b[top - 2], a4, fma(b[top], a6, v))) + (diag ? b[top - 6] : 0.0);   // v + ... + b_(top-6) I
+}
+__device__ __forceinline__ double pade_v2(const double* b, double v, double a2, double a4, double a6, int top, bool diag) {
+    return v + (fma(b[top - 4], a2, fma(b[top - 2], a4, b[top] * a6)) + (diag ? b[top - 6] : 0.0));
+}
+
+__constant__ const double kPade13[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
+                                         10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
+
+// ---- the same algorithm by one warp on matrices in shared memory: lane e (+32, +64) owns entry e of every 9x9 product.
+// Every entry is computed with the operations and the order of the serial form below (which transfer_kernel keeps, one thread
+// per job): the two agree bit for bit (tests/test_gpu_models.py::test_matrix_stage_equals_transfer_kernel).  The serial form
+// in matrix_kernel was 130 k dependent instructions of ONE lane per point: 0.2 ms of a single point's 0.67 ms device latency.
+__device__ __forceinline__ void mm9w(const double* A, const double* B, double* C, int lane) {
+    for (int e = lane; e < 81; e += 32) {
+        const int i = e / 9, j = e - 9 * i;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s = fma(A[i * 9 + k], B[k * 9 + j], s);
+        C[e] = s;
+    }
+    __syncwarp();
+}
+
+// ws: 7 x 81 doubles of shared memory; Ain, R: shared memory as well (R may not alias Ain)
+__device__ void expm9_warp(const double* Ain, double* R, double* ws, int lane) {
+    const double* b = kPade13;
+    double *A = ws, *A2 = ws + 81, *A4 = ws + 162, *A6 = ws + 243, *U = ws + 324, *V = ws + 405, *W = ws + 486;
+    double nrm = 0.0;
+    for (int j = 0; j < 9; ++j) {        // every lane: the same loop as the serial form (81 loads; keeps the order of the sums)
+        double c = 0.0;
+        for (int i = 0; i < 9; ++i) c += fabs(Ain[i * 9 + j]);
+        nrm = fmax(nrm, c);
+    }
+    int s = 0;
+    if (nrm > 5.371920351148152) s = (int)fmax(0.0, ceil(log2(nrm / 5.371920351148152)));
+    const double sc = ldexp(1.0, -s);
+    for (int e = lane; e < 81; e += 32) A[e] = Ain[e] * sc;
+    __syncwarp();
+    mm9w(A, A, A2, lane); mm9w(A2, A2, A4, lane); mm9w(A4, A2, A6, lane);
+    for (int e = lane; e < 81; e += 32) W[e] = pade_w1(b, A2[e], A4[e], A6[e], 13);
+    __syncwarp();
+    mm9w(A6, W, V, lane);
+    for (int e = lane; e < 81; e += 32) W[e] = pade_w2(b, V[e], A2[e], A4[e], A6[e], 7, e % 10 == 0);
+    __syncwarp();
+    mm9w(A, W, U, lane);
+    for (int e = lane; e < 81; e += 32) W[e] = pade_w1(b, A2[e], A4[e], A6[e], 12);
+    __syncwarp();
+    mm9w(A6, W, V, lane);
+    for (int e = lane; e < 81; e += 32) V[e] = pade_v2(b, V[e], A2[e], A4[e], A6[e], 6, e % 10 == 0);
+    __syncwarp();
+    for (int e = lane; e < 81; e += 32) { W[e] = V[e] - U[e]; R[e] = V[e] + U[e]; }
+    __syncwarp();
+    // LU with partial pivoting: lanes 0..8 own column k of W, lanes 9..17 column k of R (18 independent column updates per step)
+    for (int c = 0; c < 9; ++c) {
+        int piv = c;
+        double best = fabs(W[c * 9 + c]);
+        for (int r = c + 1; r < 9; ++r) { const double v = fabs(W[r * 9 + c]); if (v > best) { best = v; piv = r; } }
+        const double ip = 1.0 / W[piv * 9 + c];
+        double f[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) f[r] = 0.0;
+        // multipliers from the un-swapped matrix: row piv plays row c, row c plays row piv
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+            if (r > c) f[r] = W[(r == piv ? c : r) * 9 + c] * ip;
+        __syncwarp();
+        if (lane < 18) {
+            double* M = lane < 9 ? W : R;
+            const int k = lane < 9 ? lane : lane - 9;
+            if (piv != c) { const double t = M[c * 9 + k]; M[c * 9 + k] = M[piv * 9 + k]; M[piv * 9 + k] = t; }
+            if (lane >= 9 || k >= c) {
+                const double top = M[c * 9 + k];
+#pragma unroll
+                for (int r = 0; r < 9; ++r)
+                    if (r > c && f[r] != 0.0) M[r * 9 + k] = fma(-f[r], top, M[r * 9 + k]);
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < 9) {
+        const int k = lane;
+        for (int c = 8; c >= 0; --c) {
+            const double ip = 1.0 / W[c * 9 + c];
+            double v = R[c * 9 + k];
+            for (int cc = c + 1; cc < 9; ++cc) v = fma(-W[c * 9 + cc], R[cc * 9 + k], v);
+            R[c * 9 + k] = v * ip;
+        }
+    }
+    __syncwarp();
+    for (int q = 0; q < s; ++q) {
+        mm9w(R, R, W, lane);
+        for (int e = lane; e < 81; e += 32) R[e] = W[e];
+        __syncwarp();
+    }
+}
+
+// apply_transfer (below) by one warp; A and the scratch ws (9 x 81 doubles) in shared memory.  Lane 0 returns the flag.
+__device__ void apply_transfer_warp(const double* A, double t_at_tmax, const double* Y0, double* Yf /*global [9][3]*/, int* nonfinite,
+                                    double* ws, int lane) {
+    double* B = ws + 7 * 81;
+    double* R = ws + 8 * 81;
+    bool foldable = (A[0 * 9 + 0] + A[1 * 9 + 0] == 0.0);
+    for (int i = 2; i < 9; ++i) foldable = foldable && A[i * 9 + 0] == 0.0;
+    for (int i = 0; i < 9; ++i) foldable = foldable && A[i * 9 + 1] == 0.0;
+    for (int e = lane; e < 81; e += 32) {
+        const int i = e / 9, k = e - 9 * i;
+        double v = A[e];
+        if (foldable) {
+            if (k == 0 || i == 0) v = 0.0;
+            else if (i == 1) v = A[9 + k] + A[k];
+        }
+        B[e] = v;
+    }
+    __syncwarp();
+    expm9_warp(B, R, ws, lane);
+    const double ef = exp(-t_at_tmax / kTauT);
+    bool bad = false;
+    if (lane < 3) {
+        const int c = lane;
+        double y[9], z[9];
+        for (int i = 0; i < 9; ++i) y[i] = Y0[i * 3 + c];
+        y[1] += y[0]; y[0] = 0.0;
+        y[4] += (1.0 - ef) * y[3]; y[3] = ef * y[3];
+        for (int i = 0; i < 9; ++i) {
+            double v = 0.0;
+            for (int k = 0; k < 9; ++k) v = fma(R[i * 9 + k], y[k], v);
+            z[i] = v;
+        }
+        z[1] += z[0]; z[0] = 0.0;
+        z[4] += z[3]; z[3] = 0.0;
+        z[7] += z[8]; z[8] = 0.0;
+        for (int i = 0; i < 9; ++i) { Yf[i * 3 + c] = z[i]; bad |= !isfinite(z[i]); }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) *nonfinite = 1;
+}
+
 // Pade-13 scaling and squaring (Higham 2005, the algorithm behind scipy.linalg.expm used at models.py:130)
 __device__ void expm9(const double* Ain, double* R) {
-    const double b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
-                          10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
+    const double* b = kPade13;
     double A[81], A2[81], A4[81], A6[81], U[81], V[81], W[81];
     double nrm = 0.0;
     for (int j = 0; j < 9; ++j) {
@@ -1050,13 +1192,13 @@ __device__ void expm9(const double* Ain, double* R) {
     const double sc = ldexp(1.0, -s);
     for (int i = 0; i < 81; ++i) A[i] = Ain[i] * sc;
     mm9(A, A, A2); mm9(A2, A2, A4); mm9(A4, A2, A6);
-    for (int i = 0; i < 81; ++i) W[i] = b[13] * A6[i] + b[11] * A4[i] + b[9] * A2[i];
+    for (int i = 0; i < 81; ++i) W[i] = pade_w1(b, A2[i], A4[i], A6[i], 13);
     mm9(A6, W, V);   // V = A6*W (temp)
-    for (int i = 0; i < 81; ++i) W[i] = V[i] + b[7] * A6[i] + b[5] * A4[i] + b[3] * A2[i] + ((i % 10 == 0) ? b[1] : 0.0);
+    for (int i = 0; i < 81; ++i) W[i] = pade_w2(b, V[i], A2[i], A4[i], A6[i], 7, i % 10 == 0);
     mm9(A, W, U);
-    for (int i = 0; i < 81; ++i) W[i] = b[12] * A6[i] + b[10] * A4[i] + b[8] * A2[i];
+    for (int i = 0; i < 81; ++i) W[i] = pade_w1(b, A2[i], A4[i], A6[i], 12);
     mm9(A6, W, V);
-    for (int i = 0; i < 81; ++i) V[i] += b[6] * A6[i] + b[4] * A4[i] + b[2] * A2[i] + ((i % 10 == 0) ? b[0] : 0.0);
+    for (int i = 0; i < 81; ++i) V[i] = pade_v2(b, V[i], A2[i], A4[i], A6[i], 6, i % 10 == 0);
     // solve (V-U) R = (V+U) by LU with partial pivoting
     for (int i = 0; i < 81; ++i) { W[i] = V[i] - U[i]; R[i] = V[i] + U[i]; }
     for (int c = 0; c < 9; ++c) {
@@ -1072,15 +1214,15 @@ __device__ void expm9(const double* Ain, double* R) {
         for (int r = c + 1; r < 9; ++r) {
             const double f = W[r * 9 + c] * ip;
             if (f == 0.0) continue;
-            for (int k = c; k < 9; ++k) W[r * 9 + k] -= f * W[c * 9 + k];
-            for (int k = 0; k < 9; ++k) R[r * 9 + k] -= f * R[c * 9 + k];
+            for (int k = c; k < 9; ++k) W[r * 9 + k] = fma(-f, W[c * 9 + k], W[r * 9 + k]);
+            for (int k = 0; k < 9; ++k) R[r * 9 + k] = fma(-f, R[c * 9 + k], R[r * 9 + k]);
         }
     }
     for (int c = 8; c >= 0; --c) {
         const double ip = 1.0 / W[c * 9 + c];
         for (int k = 0; k < 9; ++k) {
             double v = R[c * 9 + k];
-            for (int cc = c + 1; cc < 9; ++cc) v -= W[c * 9 + cc] * R[cc * 9 + k];
+            for (int cc = c + 1; cc < 9; ++cc) v = fma(-W[c * 9 + cc], R[cc * 9 + k], v);
             R[c * 9 + k] = v * ip;
         }
     }
@@ -1239,30 +1381,38 @@ __global__ void __launch_bounds__(256) matrix_kernel(int n_points, const int32_t
                 st |= s_st[w];
             }
     }
-    if (tid != 0) return;
-    double A[81], Mp[81], Md[81];
-    for (int i = 0; i < 81; ++i) { Mp[i] = 0.0; Md[i] = 0.0; }
-    // mpdi[i][j] = sum_r pref_r(i,j) I_r with I_r = int_{Tmin}^{Tmax} Gamma_r/|dT/dt| dT > 0: the reference integrates
-    // pref*Gamma/(dT/dt) from log Tmax DOWN to log Tmin with dT/dt < 0, which is the same number (nucl.py:563-570,613)
-    for (int r = 0; r < ACRO_NR; ++r) {
-        const int j = kReacInit[r];
-        bool in_final = false;
-        for (int i = 0; i < 9; ++i)
-            if (kReacFinal[r][i] != 0) { Mp[i * 9 + j] += kReacFinal[r][i] * acc[r]; if (i == j) in_final = true; }
-        if (!in_final) Mp[j * 9 + j] += -acc[r];
+    if (warp != 0) return;
+    // warp 0: lane 0 holds the 18 integrals; rate matrices by lane 0 (a few hundred operations), the exponential and the
+    // abundances by the whole warp on matrices in shared memory
+    __shared__ double s_mx[12 * 81];
+    double* A = s_mx;
+    double* Mp = s_mx + 81;
+    double* Md = s_mx + 162;
+    if (lane == 0) {
+        for (int i = 0; i < 81; ++i) { Mp[i] = 0.0; Md[i] = 0.0; }
+        // mpdi[i][j] = sum_r pref_r(i,j) I_r with I_r = int_{Tmin}^{Tmax} Gamma_r/|dT/dt| dT > 0: the reference integrates
+        // pref*Gamma/(dT/dt) from log Tmax DOWN to log Tmin with dT/dt < 0, which is the same number (nucl.py:563-570,613)
+        for (int r = 0; r < ACRO_NR; ++r) {
+            const int j = kReacInit[r];
+            bool in_final = false;
+            for (int i = 0; i < 9; ++i)
+                if (kReacFinal[r][i] != 0) { Mp[i * 9 + j] += kReacFinal[r][i] * acc[r]; if (i == j) in_final = true; }
+            if (!in_final) Mp[j * 9 + j] += -acc[r];
+        }
+        const double In = (kHbar / kTauN) * acc[ACRO_NR], It = (kHbar / kTauT) * acc[ACRO_NR];
+        Md[0 * 9 + 0] = -In; Md[1 * 9 + 0] = In;    // n -> p
+        Md[3 * 9 + 3] = -It; Md[4 * 9 + 3] = It;    // t -> He3
     }
-    const double In = (kHbar / kTauN) * acc[ACRO_NR], It = (kHbar / kTauT) * acc[ACRO_NR];
-    Md[0 * 9 + 0] = -In; Md[1 * 9 + 0] = In;    // n -> p
-    Md[3 * 9 + 3] = -It; Md[4 * 9 + 3] = It;    // t -> He3
-    for (int i = 0; i < 81; ++i) A[i] = Mp[i] + Md[i];
-    if (mpdi_out) for (int i = 0; i < 81; ++i) mpdi_out[(int64_t)pt * 81 + i] = Mp[i];
-    if (mdcy_out) for (int i = 0; i < 81; ++i) mdcy_out[(int64_t)pt * 81 + i] = Md[i];
+    __syncwarp();
+    for (int i = lane; i < 81; i += 32) {
+        A[i] = Mp[i] + Md[i];
+        if (mpdi_out) mpdi_out[(int64_t)pt * 81 + i] = Mp[i];
+        if (mdcy_out) mdcy_out[(int64_t)pt * 81 + i] = Md[i];
+    }
+    __syncwarp();
     int bad = 0;
-    if (Yf_out) {
-        double Yf[27];
-        apply_transfer(A, pt_t_at_tmax[pt], t.Y0, nullptr, Yf, &bad);
-        for (int i = 0; i < 27; ++i) Yf_out[(int64_t)pt * 27 + i] = Yf[i];
-    }
+    if (Yf_out) apply_transfer_warp(A, pt_t_at_tmax[pt], t.Y0, Yf_out + (int64_t)pt * 27, &bad, s_mx + 3 * 81, lane);
+    if (lane != 0) return;
     if (bad) st |= ACRO_ST_NONFINITE;
     if (pt_e0 && (double)(int)pt_e0[pt] > 1e3) st |= ACRO_ST_E0_ABOVE_GEV;
     if (status_out) status_out[pt] = st;

@@ -433,3 +433,13 @@ def test_closed_form_photon_plane_corners(gpu_engine, xcheck_engine):
             assert Kf[1][i, j] > 0
     finally:
         params.Ephb_T_max = old_cut
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", POINTS)
+def test_matrix_stage_equals_transfer_kernel(gpu_engine, results, name):
+    """matrix_kernel exponentiates by one warp on shared-memory matrices (expm9_warp), transfer_kernel by one thread per job
+    (expm9): the same operations in the same order per matrix entry, so the abundances agree bit for bit."""
+    z, sp, r = results[name]
+    Y = gpu_engine.transfer(r["mpdi"].reshape(1, 9, 9), r["mdcy"].reshape(1, 9, 9), 1.0, sp.t_at_tmax)
+    assert np.array_equal(Y[0], r["Yf"].reshape(-1, 9, 3)[0])
