@@ -1295,8 +1295,8 @@ __device__ __forceinline__ double pow10_segment(double alpha, double beta, doubl
     return ln10 * bot * dx * phi;
 }
 
-// One block per point: one warp when the batch has many points, eight warps when it has few (a single point would otherwise
-// spend 0.7 ms in ONE warp walking its ~2000 cosmo-table cells: half of the device latency of a run_disintegration() call).
+// One block of eight warps per point (a single point would otherwise spend 0.7 ms in ONE warp walking its ~2000 cosmo-table
+// cells: half of the device latency of a run_disintegration() call).
 // Integrates Gamma_r(T) T / |dT/dt| dlogT exactly: both factors are piecewise power laws (log10-log10 linear on the NT-point
 // rate grid, utils.py:38-61, and on the cosmo table, input.py:205-226), so each sub-cell has the closed form of
 // pow10_segment; no quadrature (the reference uses QAGS, nucl.py:613-614).
@@ -1610,7 +1610,10 @@ cudaError_t launch_matrix(int n_points, const int32_t* pt_nt, const int32_t* pt_
         cudaError_t e = cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int threads = n_points >= 2 * sm_count() ? 32 : 256;     // few points: eight warps share a point's cosmo cells
+    // eight warps share a point's ~2000 cosmo-table cells, whatever the batch size (one warp per point for large batches was
+    // 0.83 against 0.43 ms per 1000-point slice once the exponential no longer ran in one lane); the partition of the cells and
+    // with it the rounding of the 18 integrals is then the same for a single point and for a scan
+    const int threads = 256;
     matrix_kernel<<<n_points, threads, smem, st>>>(n_points, pt_nt, pt_sys_off, sys_T, pdi, T_lo, pt_t_at_tmax, status_sys, pt_e0,
                                                    mpdi, mdcy, Yf, status, t, p);
     lc.launches++;
