@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
     const double* g = G + b.sys_f_off[s] * 3;
     // per-warp shared memory: lnF[ne] | wF[3][ne] during the back-substitution; afterwards the wF region is reused for
     // lnE[ne] and the 17x32 rate accumulators (stride = ne_max + max(3 ne_max, ne_max + 17*32))
-    double* lnF = smem + (size_t)wib * smem_stride;   // [ne]  log of the floored photon spectrum
+    double* lnF = smem + (size_t)wib * smem_stride;   // [ne]  floored photon spectrum during the solve, its log afterwards
     double* wF  = lnF + ne;                           // [3][ne]
     double* lnE = wF;                                 // [ne]   (after the solve)
     const int64_t np = b.n_pairs_total;
@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
             if (Ei < EX) F = SN * K0u * pow(EX / Ei, 1.5) / g[i];
             else if (Ei <= (1.0 + 5e-2) * EC) F = SN * K0u * pow(EX / Ei, 2.0) / g[i];
             F = fmax(F, p.approx_zero);
-            lnF[i] = log(F);
+            lnF[i] = F;
             if (fo) { fo[i] = F; fo[ne + i] = p.approx_zero; fo[2 * ne + i] = p.approx_zero; }
         }
         __syncwarp();
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
             wF[top]          = S0[0] / G0 + hw * F[0];
             wF[ne + top]     = S0[1] / G1 + hw * F[1];
             wF[2 * ne + top] = S0[2] / G2 + hw * F[2];
-            lnF[top] = log(fmax(F[0], p.approx_zero));
+            lnF[top] = fmax(F[0], p.approx_zero);
             if (fo) {
                 fo[top] = fmax(F[0], p.approx_zero);
                 fo[ne + top] = fmax(F[1], p.approx_zero);
@@ -813,7 +813,8 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
         if (lane == 0) {
             const double w = dy * Ei;
             wF[i] = w * F[0]; wF[ne + i] = w * F[1]; wF[2 * ne + i] = w * F[2];
-            lnF[i] = log(fmax(F[0], p.approx_zero));
+            lnF[i] = fmax(F[0], p.approx_zero);     // the logarithm is taken after the loop, by all lanes: one log per row on
+                                                     // lane 0 was ~300 cycles on the critical path of every row
             if (fo) {
                 fo[i] = fmax(F[0], p.approx_zero);
                 fo[ne + i] = fmax(F[1], p.approx_zero);
@@ -824,7 +825,10 @@ __global__ void __launch_bounds__(128, ACRO_SV_MINBLOCKS) solve_pdi_kernel(acro_
     }
     }   // !universal
     if (!pdi) return;
-    for (int i = lane; i < ne; i += 32) lnE[i] = log(E[i]);     // wF is dead from here on
+    for (int i = lane; i < ne; i += 32) {     // wF is dead from here on
+        lnF[i] = log(lnF[i]);
+        lnE[i] = log(E[i]);
+    }
     __syncwarp();
 
     // --- photodisintegration rates (nucl.py:398-467)
