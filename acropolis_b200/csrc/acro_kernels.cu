@@ -2,21 +2,23 @@
 //
 //   rates_kernel        thread per (system, E_i)        G[3,NE]: closed forms + rates.db bilinear interpolation
 //   direct_rates_kernel warp per out-of-table (E,T)     the two 2-D rate integrals the reference does with dblquad
-//   pair_closed_forms_kernel / kernels_mma_kernel / kernels_wien_kernel
-//                                                       the production kernel builder (acro_tmma.cuh, acro_tshared.cuh): five
-//                                                       K planes, closed forms + three Planck-weighted integrals on a
-//                                                       temperature-shared grid contracted with DMMA / Gauss-Laguerre on
-//                                                       the Wien tail
+//   pair_closed_forms_kernel, ic_photon_closed_kernel, kernels_mma_kernel<KIND>, kernels_wien_kernel<Q,KIND>
+//                                                       the production kernel builder (acro_icphoton.cuh, acro_tmma.cuh,
+//                                                       acro_tshared.cuh): five K planes -- closed forms per pair; the
+//                                                       e -> gamma integral from tabulated one-variable functions; the
+//                                                       e -> e and gamma -> e integrals on a temperature-shared grid
+//                                                       contracted with DMMA, Gauss-Laguerre on their Wien tail
 //   kernels_kernel      thread per (system, E_i, E_j>=i) cross-check modes, only with -DACRO_CROSSCHECK (the test build):
 //                                                       fixed-order Gauss-Legendre in log(eps_bar) per (E,E',T)
 //                                                       (PLAIN_GL with the reference's F/G, PER_T reduced)
 //   solve_pdi_kernel    warp per system                 back-substitution of the 3-species cascade equation,
 //                                                       fused with the 17 sigma(E)*F(E) rate integrals
-//   matrix_kernel       warp per point                  exact piecewise T-integral, 9x9 expm, decay matrices, Yf
+//   matrix_kernel       block (8 warps) per point       exact piecewise T-integral; 9x9 expm, decay matrices, Yf by warp 0
 //   transfer_kernel     thread per matrix               fast-parameter path: expm(f*mpdi+mdcy) and Yf only
 //
-// None of this is a dense contraction, so no tensor-core (tcgen05) path exists for it: the bound is the FP64 pipe
-// for the quadrature kernels and HBM for solve/matrix.
+// The sum over grid nodes of the shared-grid kernels is a dense FP64 contraction and runs on the FP64 tensor path
+// (mma.sync m8n8k4 f64 -> DMMA; tcgen05 has no FP64 type); the bound is the FP64 pipe -- which DFMA and DMMA share on
+// B200 -- for the quadrature kernels and HBM for the solve.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(128, ACRO_KK_MINBLOCKS) kernels_kernel(acro_ba
     KernelEntry k;
     if (FAST) {
         SharedInfo si;
-        si.on = false;   // per-(pair,T) evaluation only (ACRO_KERNELS_PER_T); the FAST mode runs kernels_shared_kernel instead
+        si.on = false;   // per-(pair,T) evaluation only (ACRO_KERNELS_PER_T); the FAST mode runs kernels_mma_kernel instead
         const int s_first = b.pt_sys_off[pt], nt = b.pt_nt[pt];
         si.Tmin = b.sys_T[s_first];
         const SharedGrid g = shared_grid(si.Tmin, b.sys_T[s_first + nt - 1], eg[ne - 1], p.Ephb_T_max);

@@ -1,9 +1,8 @@
-// acro_tmma.cuh -- the production kernel builder: temperature-shared evaluation of the three thermal kernel integrals with the
-// temperature accumulation on the FP64 tensor-core path (DMMA, mma.sync m8n8k4 f64).
+// acro_tmma.cuh -- the production kernel builder for the e -> e and gamma -> e thermal kernel integrals: temperature-shared
+// evaluation with the temperature accumulation on the FP64 tensor-core path (DMMA, mma.sync m8n8k4 f64).  (The e -> gamma
+// integral needs no quadrature: acro_icphoton.cuh.)
 //
-// Same integrals, same panel grid, same limits, same Bose table and partial-panel machinery as the other two forms of the
-// shared kernel (acro_tshared.cuh: one thread per pair; acro_tshared4.cuh: four lanes per pair, FMAs) -- what changes is who
-// does the sum over grid nodes.  For one model point
+// Panel grid, limits, Bose table and partial-panel machinery: acro_tshared.cuh.  For one model point
 //
 //        I[pair][T] = sum_node  W[pair][node] * B[node][T]
 //
@@ -11,19 +10,18 @@
 // B = the Bose table of the temperature tile in shared memory: a dense FP64 contraction of shape (pairs x 12) x (12 x 40) per
 // panel.  On B200 DMMA and DFMA share one pipe (tools/microbench/fp64_pipes.cu: 37.0 vs 34.1 TFLOP/s alone, 33-34 mixed), so
 // the tensor path adds no flops -- but one DMMA.8x8x4 replaces 8 DFMA issue slots and, with the fragment layout below, the
-// five 16-byte Bose loads + one weight load per ten FMAs of the four-lane form become one 8-byte load per DMMA; the weights
+// five 16-byte Bose loads + one weight load per ten FMAs of round 1's FMA form become one 8-byte load per DMMA; the weights
 // never pass through shared memory at all:
 //
-//   lane = 4 g + q  (g = 0..7, q = 0..3) owns the pairs 2g and 2g+1 of the warp's current 16 pairs (two M-tiles of 8 pairs)
+//   lane = 4 g + q  (g = 0..7, q = 0..3) works for pair g of the warp's current 8 pairs (one M-tile; two M-tiles per warp were
+//                                    measured: spills, slower)
 //   A fragment (8 pairs x 4 nodes):  lane holds W[pair g][node q + 4 ks]  -> the lane EVALUATES nodes q, q+4, q+8 of a panel
-//                                    for its two pairs and the values are the A fragments of the three k-steps as they are;
-//   B fragment (4 nodes x 8 T):      lane loads B[node q + 4 ks][T = 8 nt + g] from the shared-memory table (shared by both
-//                                    M-tiles);
-//   C fragment (8 pairs x 8 T):      lane accumulates I[pair g][T = 8 nt + 2q + {0,1}]: 5 N-tiles x 2 M-tiles = 20 doubles.
+//                                    for its pair and the values are the A fragments of the three k-steps as they are;
+//   B fragment (4 nodes x 8 T):      lane loads B[node q + 4 ks][T = 8 nt + g] from the shared-memory table;
+//   C fragment (8 pairs x 8 T):      lane accumulates I[pair g][T = 8 nt + 2q + {0,1}]: 5 N-tiles = 10 doubles.
 //
-// Stores: the lane's two pairs are neighbours in the packed triangle, so every result leaves as a 16-byte store and the 8
-// lanes of one q write 128 contiguous bytes per temperature (the K planes are padded so that every system starts on a
-// 32-byte boundary: sector-aligned, no partial-sector read-modify-write in DRAM).
+// Stores: the 8 pairs of a sub-pass are neighbours in the packed triangle: 64 contiguous bytes per temperature (the K planes
+// are padded so that every system starts on a 32-byte boundary: sector-aligned, no partial-sector read-modify-write in DRAM).
 #pragma once
 #include "acro_tshared.cuh"
 
@@ -161,8 +159,9 @@ __global__ void __launch_bounds__(128) pair_closed_forms_kernel(acro_batch_t b, 
 // One launch per integral kind (KIND = KIND_IC_PHOTON -> plane 1, KIND_IC_ELECTRON -> plane 4, KIND_PC_ELECTRON -> planes 3, 2
 // and the closed-form plane 0).  Three specialised kernels instead of one that loops over the kinds: the integrand is a
 // compile-time choice (no dispatch in the node loops, a third of the code per kernel), the pair constants shrink to 8 fields,
-// and the three launches together are 10 % faster than the fused kernel although each fills its own Bose table
-// (21.8 against 24.4 ms per 1000-point slice; with 2 passes per block, the fused kernel's optimum, the split form LOSES).
+// and three launches together were 10 % faster than the fused kernel although each fills its own Bose table (21.8 against
+// 24.4 ms per 1000-point slice; with 2 passes per block, the fused kernel's optimum, the split form LOSES).  Production
+// launches KIND_IC_ELECTRON and KIND_PC_ELECTRON; the KIND_IC_PHOTON instantiation is not launched any more.
 template <int KIND>
 __global__ void __launch_bounds__(kMmThreads, 1) kernels_mma_kernel(acro_batch_t b, double* __restrict__ Kws,
                                                                     const double* __restrict__ closed, DeviceTables tb,

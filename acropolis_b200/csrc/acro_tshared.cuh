@@ -11,15 +11,16 @@
 //     some temperature still sees the Planck roll-off), 2 e-folds wide below, down to log(Tmin) - 25 (what lies below
 //     contributes < 2e-11; what lies above 50 Tmax < 3e-19);
 //   * per temperature tile the Bose factors at the grid nodes are staged in SHARED MEMORY once per thread block and serve
-//     several passes of 512 pairs -- the "thermal-photon grid" of BASELINE.json:north_star;
+//     up to 48 passes of 512 pairs -- the "thermal-photon grid" of BASELINE.json:north_star;
 //   * f is evaluated once per (pair, node) and contracted with the Bose table over the nodes for all temperatures of the
 //     tile; the panel that contains the lower limit is integrated on its own nodes against the Legendre expansion of the Bose
 //     factor (exact for what the panel rule itself resolves), and so is the panel that contains the upper limit when that is
 //     the kinematic one (x_b0 < 200 T); the thermal cut-off 200 T is applied as zeros in the Bose table.
 //
-// kernels_mma_kernel writes all five planes (closed forms included); kernels_wien_kernel then overwrites the (pair, T)
-// combinations beyond wien_from * T with its own Gauss-Laguerre rule (acro_fastquad.cuh).  Both evaluate the regime predicates
-// with the same expressions on the same numbers.
+// kernels_mma_kernel (one launch for the e -> e plane, one for the gamma -> e planes and the closed-form gamma -> gamma
+// plane) writes every entry of its planes; kernels_wien_kernel then overwrites the (pair, T) combinations beyond
+// wien_from * T with its own Gauss-Laguerre rule (acro_fastquad.cuh).  Both evaluate the regime predicates with the same
+// expressions on the same numbers.  The e -> gamma plane comes from ic_photon_closed_kernel (acro_icphoton.cuh).
 //
 // Tuning constants (each is a -D macro so that tools/gpu_ab_variants.py can time a variant library; values = measured best
 // on the 840-point benchmark slice in round 1):
@@ -124,9 +125,9 @@ __device__ __forceinline__ int panel_of(const SharedGrid& g, double y) {   // pa
 
 // Second kernel of the production path: the (pair, T) combinations that the shared grid does not serve (lower limit on
 // the Wien tail) get their own Gauss-Laguerre / Gauss-Legendre rule (acro_fastquad.cuh), written over / added to what
-// kernels_shared_kernel left in the planes.
+// kernels_mma_kernel left in the planes.
 //
-// Work distribution: a thread owns one (E,E') pair of a point; for each of the three integrals the temperatures it has to
+// Work distribution: a thread owns one (E,E') pair of a point; for the launch's integral the temperatures it has to
 // do form a contiguous index range (temperatures ascend, all predicates are monotone).  The ranges differ a lot between
 // the 32 pairs of a warp (ncu: 15.6 of 32 lanes active when every lane simply loops over its own range), so the warp
 // pools its items: exclusive prefix sum of the range lengths, then 32 items at a time, each lane fetching the constants
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(128, ACRO_WT_MINBLOCKS) kernels_wien_kernel(ac
     const double pre_ic = 2.0 * kPi * a2 / (Ep * Ep), pre_pc = 0.25 * kPi * a2 * kMe2 / (Ep * Ep * Ep);
     const double xf = p.Ephb_T_max;
     // range of temperature indices that this pair has to do for one integral: [first non-empty range, first T that the
-    // shared grid serves) -- the predicates are the expressions used by kernels_shared_kernel, evaluated on the same T
+    // shared grid serves) -- the predicates are the expressions used by kernels_mma_kernel, evaluated on the same T
     auto range = [&](double x_a, double x_b0, bool has, int t_extra, int& t_lo, int& n) {
         t_lo = 0; n = 0;
         if (!valid || !has || !(x_b0 > x_a)) return;
