@@ -104,16 +104,20 @@ class Engine(object):
     _cache = {}
 
     @classmethod
-    def get(cls, ii, device=None, variant="product"):
+    def get(cls, ii, device=None, variant="product", lane=0):
         """The engine of (device, input tables).  ``variant="xcheck"`` binds the test build of the library, which also has
-        the per-(E,E',T) cross-check kernel modes (params.kernel_mode = PLAIN_GL / PER_T)."""
+        the per-(E,E',T) cross-check kernel modes (params.kernel_mode = PLAIN_GL / PER_T).  ``lane`` > 0 gives a sibling engine
+        on the same device with its own library handle, stream, staging arenas and workspace: what two engines launch overlaps
+        on the GPU (``scans.run_points`` alternates its groups between lanes 0 and 1)."""
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
-        key = (device.index, id(ii), flags.usedb, variant)
+        key = (device.index, id(ii), flags.usedb, variant, lane)
         eng = cls._cache.get(key)
         if eng is None:
             eng = cls._cache[key] = cls(ii, device, variant)
+            if lane:
+                cls.get(ii, device, variant)._siblings.append(eng)
         return eng
 
     def __init__(self, ii, device, variant="product"):
@@ -154,6 +158,7 @@ class Engine(object):
         self._arena = _Arena(device)
         self._ws = None
         self._params_key = None
+        self._siblings = []          # engines of other lanes on this device (their launches count as this engine's)
 
     def __del__(self):
         try:
@@ -178,7 +183,7 @@ class Engine(object):
             self._params_key = key
 
     def launch_count(self):
-        return int(self.lib.acro_launch_count(self.h))
+        return int(self.lib.acro_launch_count(self.h)) + sum(e.launch_count() for e in self._siblings)
 
     def measure_fp64_peak(self):
         v = C.c_double()

@@ -196,19 +196,21 @@ def run_models(models, devices=None, want_matp=False):
     return (Yf, matp) if want_matp else Yf
 
 
-def run_points(model, param_sets, devices=None, group=4096, first_group=64, growth=64):
+def run_points(model, param_sets, devices=None, group=4096, first_group=40, growth=5, lanes=2):
     """Rows ``[sorted params..., 9 mean, 9 high, 9 low]`` for an arbitrary list of parameter dicts of one model class
     (or ``functools.partial``): the batched form of ``BufferedScanner._run_single`` (reference scans.py:110-124).
     Builds the models, stages their grids and source arrays, runs the CUDA path and reads the abundances back.  On one
     device the list is processed in groups: while the GPU works on one group the host constructs the models and source
     arrays of the next.  The first group is the LAST `first_group` GPU points of the list, launched before anything else
-    is constructed (scans are ordered by increasing mass, so the tail is the expensive end: 64 points of the benchmark
-    scan's tail are ~10 ms of GPU work, what the host needs for the other 936); the rest is sorted heaviest-first by
-    the cost proxy NT * NE^2 and goes in groups that grow by `growth` up to `group`.  Any order is valid -- a list whose
-    tail is cheap only pipelines less well.  Measured on 1000-point slices (tools/gpu_e2e_timeline.py; host ~12 us per
-    point, GPU ~47 us on average): two launch sets cost ~3.5 ms more GPU time than one (the tails of the long-block
-    builder kernels twice), so two groups are the sweet spot, and first_group = 64 is the best split (wall per call: 32:
-    48.2 ms with a 4 ms GPU gap, 48: 45.8, 64: 44.4, 96: 46.1, 128: 46.3, 192: 49.0)."""
+    is constructed (scans are ordered by increasing mass, so the tail is the expensive end); the rest is sorted
+    heaviest-first by the cost proxy NT * NE^2 and goes in groups that grow by `growth` up to `group`.  Consecutive groups go to
+    different engine lanes (``Engine.get(..., lane=k)``: own library handle, stream and workspace), so their kernels OVERLAP on
+    the GPU: a small group alone leaves 40 % of the device idle (wave quantisation and tails of the long-block builder kernels),
+    the next group fills it.  Any order is valid -- a list whose tail is cheap only pipelines less well.  Measured on 1000-point
+    slices (tools/gpu_e2e_timeline.py; host ~12 us per point, GPU ~45 us on average), wall per call: one lane, groups 64 + 776:
+    44.0 ms (two launch sets one after the other cost 3.5 ms more GPU time than one); two lanes, 64 + 256 + 520: 43.0;
+    48 + 192 + 600: 42.4; **40 + 200 + 600: 41.8**; 32 + 128 + 512 + 168: 43.4; three lanes: no better; one lane with three
+    groups: 48 ms.  A single launch set of all 840 points is 38.1 ms of GPU time."""
     import torch
     if devices is None:
         dist = _dist_world()
@@ -226,13 +228,13 @@ def run_points(model, param_sets, devices=None, group=4096, first_group=64, grow
     gc_was_on = gc.isenabled()
     gc.disable()
     try:
-        return _run_points_pipelined(model, param_sets, devices, group, first_group, growth, rows, eng, in_flight)
+        return _run_points_pipelined(model, param_sets, devices, group, first_group, growth, rows, eng, in_flight, lanes)
     finally:
         if gc_was_on:
             gc.enable()
 
 
-def _run_points_pipelined(model, param_sets, devices, group, first_group, growth, rows, eng, in_flight):
+def _run_points_pipelined(model, param_sets, devices, group, first_group, growth, rows, eng, in_flight, lanes=2):
     N = len(param_sets)
 
     # rows [N, n_params + 9 ncol]: the parameter columns are filled while the GPU works, the abundance columns of a group in
@@ -249,13 +251,14 @@ def _run_points_pipelined(model, param_sets, devices, group, first_group, growth
         return table[0]
 
     def finish(entry):
-        idx, pend = entry
-        out = eng.collect(pend, want=("Yf", "status"))
+        idx, pend, e = entry
+        out = e.collect(pend, want=("Yf", "status"))
         statuses.append(out["status"])
         t = ensure_table(ncol)
         t[np.asarray(idx), len(keys):] = out["Yf"][:, :, :ncol].transpose(0, 2, 1).reshape(len(idx), 9 * ncol)
 
     models, ncol, statuses, direct = [None] * N, 3, [], []
+    engines, n_submitted = [], [0]
 
     def build(i):
         """Model of point i; a point below all thresholds is answered on the spot (a scan may start with hundreds)."""
@@ -270,14 +273,19 @@ def _run_points_pipelined(model, param_sets, devices, group, first_group, growth
         if eng is None:
             ncol = m._sII.bbn_abundances().shape[1]
             eng = Engine.get(m._sII, devices[0])
-            eng.last_h2d_bytes = eng.last_d2h_bytes = 0
+            engines.append(eng)
+            engines.extend(Engine.get(m._sII, devices[0], lane=k) for k in range(1, max(1, lanes)))
+            for e in engines:
+                e.last_h2d_bytes = e.last_d2h_bytes = 0
         return True
 
     def submit(idx):
         todo = [models[i] for i in idx]
         specs = type(todo[0]).point_specs(todo) if len({type(mm) for mm in todo}) == 1 else [mm.point_spec() for mm in todo]
-        in_flight.append((idx, eng.submit(specs, want=("Yf", "status"))))
-        while len(in_flight) > 2:
+        e = engines[n_submitted[0] % len(engines)]      # consecutive groups on different lanes: their kernels overlap on the GPU
+        n_submitted[0] += 1
+        in_flight.append((idx, e.submit(specs, want=("Yf", "status")), e))
+        while len(in_flight) > 2 * len(engines):
             finish(in_flight.pop(0))
 
     # 1. first group: the last `first_group` GPU points of the list, before anything else is even constructed
@@ -303,6 +311,9 @@ def _run_points_pipelined(model, param_sets, devices, group, first_group, growth
             target = min(group, growth * target)
     for entry in in_flight:
         finish(entry)
+    for e in engines[1:]:                                # the caller reads the transfer counters of the primary engine
+        eng.last_h2d_bytes += e.last_h2d_bytes
+        eng.last_d2h_bytes += e.last_d2h_bytes
     if statuses:
         report_status(np.concatenate(statuses), "acropolis_b200.scans.run_points")
     # A model holds lists of its own bound methods (get_source_terms, as in the reference): a reference cycle per point that

@@ -17,21 +17,21 @@ orig_launch = Engine.launch
 def launch(self, ch, stages=7 | 8):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(self.stream); orig_launch(self, ch, stages); b.record(self.stream)
-    evs.append((a, b, ch["cnt"]["n_points"], time.perf_counter()))
+    evs.append((a, b, ch["cnt"]["n_points"], time.perf_counter()))     # with lanes > 1 the groups overlap: the gaps are not idle time
 Engine.launch = launch
 import itertools
-CFG = [(fg, 64) for fg in (32, 48, 64, 96, 128, 192)]
-for (fg, gr), rep in itertools.product(CFG, range(4)):
+CFG = [(40, 5, 2)]     # (first_group, growth, lanes): the defaults of run_points
+for (fg, gr, ln), rep in itertools.product(CFG, range(4)):
     par = slice_params(pts, rep)
     torch.cuda.synchronize()
     del evs[:]
     t0 = time.perf_counter()
     z = torch.cuda.Event(enable_timing=True); z.record(torch.cuda.current_stream())
-    rows = run_points(model, par, devices=[0], first_group=fg, growth=gr)
+    rows = run_points(model, par, devices=[0], first_group=fg, growth=gr, lanes=ln)
     t1 = time.perf_counter()
     torch.cuda.synchronize()
     if rep >= 2:
-        print("first_group %d growth %d:" % (fg, gr), "call %.1f ms wall; groups (points, host launch time since start [ms], GPU ms, idle gap before [ms]):" % (1e3 * (t1 - t0)))
+        print("first_group %d growth %d lanes %d:" % (fg, gr, ln), "call %.1f ms wall; groups (points, host launch time since start [ms], GPU ms, idle gap before [ms]):" % (1e3 * (t1 - t0)))
         prev = None
         for a, b, n, th in evs:
             gap = prev.elapsed_time(a) if prev is not None else float("nan")
