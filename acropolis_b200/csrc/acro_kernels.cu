@@ -1523,10 +1523,7 @@ cudaError_t launch_kernels(const acro_batch_t& b, const DeviceTables& t, const a
         // threads, ms per 1000-point slice with three integrals: 1: 28.5, 2: 24.8, 4: 22.9, 8: 19.8, 12: 19.6; with two: 8: 13.6, 12: 13.5,
         // 16: 13.4, 24: 13.1, 32: 12.8, 48: 12.7 -- a block drains once, when its slowest warp is done), fewer while that would leave less
         // than two blocks per SM (single points and short batches: latency, not throughput)
-#ifndef ACRO_MM_MINWAVES
-#define ACRO_MM_MINWAVES 2
-#endif
-        const int ppb = (int)std::max<int64_t>(1, std::min<int64_t>(kMmPassesPerBlock, (int64_t)b.n_points * passes_max / (ACRO_MM_MINWAVES * (int64_t)sm_count())));
+        const int ppb = (int)std::max<int64_t>(1, std::min<int64_t>(kMmPassesPerBlock, (int64_t)b.n_points * passes_max / (2 * (int64_t)sm_count())));
         dim3 grid((unsigned)((passes_max + ppb - 1) / ppb), (unsigned)b.n_points);
         // function attributes are per device (each primary context has its own CUfunction): set before every launch
         cudaError_t e = cudaSuccess;
