@@ -18,7 +18,7 @@ def install_as(name="acropolis"):
     pkg = _sys.modules[__name__]
     _sys.modules[name] = pkg
     for sub in ("params", "flags", "info", "pprint", "input", "db", "utils", "cascade", "nucl", "models", "scans",
-                "ext", "ext.models", "ext.benchmarks"):
+                "obs", "plots", "ext", "ext.models", "ext.benchmarks"):
         try:
             _sys.modules[name + "." + sub] = importlib.import_module(__name__ + "." + sub)
         except ImportError:
