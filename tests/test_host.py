@@ -519,3 +519,55 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                         capture_output=True, text=True, timeout=120, env=env1, cwd=ROOT)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_run_points_groups_and_lanes_with_a_stub_engine(monkeypatch):
+    """scans.run_points without a GPU: the engine is replaced by a stub that records what is submitted to which lane and
+    answers Yf[p] = f(E0, number of temperatures).  Checks the pipelining logic itself: the first group is the tail of the list,
+    the rest goes heaviest-first in groups of growth x the previous size, consecutive groups alternate between the lanes,
+    every GPU point is submitted exactly once, trivial points never reach the engine, and the rows come back in input order."""
+    from functools import partial
+    import acropolis_b200.scans as scans
+    from acropolis_b200.models import DecayModel
+    calls = []
+
+    class StubEngine(object):
+        engines = {}
+
+        @classmethod
+        def get(cls, ii, device=None, variant="product", lane=0):
+            return cls.engines.setdefault(lane, cls(lane))
+
+        def __init__(self, lane):
+            self.lane, self.last_h2d_bytes, self.last_d2h_bytes = lane, 0, 0
+
+        def submit(self, specs, want=("Yf", "status")):
+            calls.append((self.lane, [(s.E0, len(s.T)) for s in specs]))
+            self.last_h2d_bytes += 8 * len(specs)
+            return [specs]
+
+        def collect(self, pend, want=("Yf", "status")):
+            specs = pend[0]
+            Y = np.array([[[s.E0 * (1 + i) + 0.001 * len(s.T) + 10 * c for c in range(3)] for i in range(9)] for s in specs])
+            return dict(Yf=Y, status=np.zeros(len(specs), dtype=np.int32))
+
+    monkeypatch.setattr(scans, "Engine", StubEngine)
+    mphi = np.logspace(0, 3, 30)                      # the first points are below every threshold (E0 = mphi/2 < 1.5)
+    tau = np.logspace(3, 10, 13)
+    par = [dict(mphi=float(m), tau=float(t)) for m in mphi for t in tau]
+    model = partial(DecayModel, temp0=10., n0a=1e-10, bree=0., braa=1.)
+    rows = scans.run_points(model, par, devices=[0], first_group=16, growth=4, lanes=2)
+    n_trivial = sum(1 for p in par if p["mphi"] / 2 <= 1.5)
+    sizes = [len(c[1]) for c in calls]
+    assert sizes[0] == 16 and sizes[1] == 64 and sum(sizes) == len(par) - n_trivial and n_trivial > 0
+    assert [c[0] for c in calls] == [k % 2 for k in range(len(calls))]                  # lanes alternate
+    first = calls[0][1]
+    assert sorted(e0 for e0, _ in first) == sorted(p["mphi"] / 2 for p in par[-16:])  # the tail of the list goes first
+    cost = [nt * max(int(np.log10(e0 / 1.5) * 120), 10) ** 2 for e0, nt in calls[1][1]]
+    assert cost == sorted(cost, reverse=True)                                          # heaviest first within the rest
+    assert rows.shape == (len(par), 2 + 27)
+    for r, p in zip(rows, par):
+        assert r[0] == p["mphi"] and r[1] == p["tau"]
+        if p["mphi"] / 2 > 1.5:
+            assert abs(r[2] - (p["mphi"] / 2 + 0.001 * 40)) < 0.0011 and abs(r[2 + 9] - r[2] - 10.0) < 1e-9   # Yf[0, col 0] and [0, col 1] of the stub
+    assert StubEngine.engines[0].last_h2d_bytes == 8 * (len(par) - n_trivial)          # lane 1's counters are folded into lane 0's
