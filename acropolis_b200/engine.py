@@ -117,7 +117,8 @@ class Engine(object):
         if eng is None:
             eng = cls._cache[key] = cls(ii, device, variant)
             if lane:
-                cls.get(ii, device, variant)._siblings.append(eng)
+                eng._primary = cls.get(ii, device, variant)
+                eng._primary._siblings.append(eng)
         return eng
 
     def __init__(self, ii, device, variant="product"):
@@ -159,6 +160,7 @@ class Engine(object):
         self._ws = None
         self._params_key = None
         self._siblings = []          # engines of other lanes on this device (their launches count as this engine's)
+        self._primary = None         # set on a sibling: the lane-0 engine of its device
 
     def __del__(self):
         try:
@@ -262,10 +264,11 @@ class Engine(object):
         """Greedy split of the point list so that each chunk's workspace fits the budget."""
         if budget is None:
             budget = params.workspace_bytes
-            if budget is None:      # default: 40% of the device memory that is free at first use, at most 64 GiB
-                if not hasattr(self, "_auto_budget"):
+            if budget is None:      # default: 40% of the device memory that is free at first use, at most 64 GiB,
+                if not hasattr(self, "_auto_budget"):      # shared between the lanes that exist on the device by then
                     free, _ = torch.cuda.mem_get_info(self.device)
-                    self._auto_budget = int(min(64 * 1024**3, 0.4 * free))
+                    n_lanes = 1 + len((self._primary or self)._siblings)
+                    self._auto_budget = int(min(64 * 1024**3, 0.4 * free) / n_lanes)
                 budget = self._auto_budget
         out, cur, acc = [], [], 0
         for i, p in enumerate(points):
