@@ -209,7 +209,8 @@ def run_points(model, param_sets, devices=None, group=4096, first_group=40, grow
     the next group fills it.  Any order is valid -- a list whose tail is cheap only pipelines less well.  Measured on 1000-point
     slices (tools/gpu_e2e_timeline.py; host ~12 us per point, GPU ~45 us on average), wall per call: one lane, groups 64 + 776:
     44.0 ms (two launch sets one after the other cost 3.5 ms more GPU time than one); two lanes, 64 + 256 + 520: 43.0;
-    48 + 192 + 600: 42.4; **40 + 200 + 600: 41.8**; 32 + 128 + 512 + 168: 43.4; three lanes: no better; one lane with three
+    48 + 192 + 600: 42.4; **40 + 200 + 600: 41.8**; 32 + 160 + 648: 42.2; 24 + 120 + 600 + 96: 42.9; 16 + 80 + 400 + 344: 44.4;
+    three lanes: no better; one lane with three
     groups: 48 ms.  A single launch set of all 840 points is 38.1 ms of GPU time."""
     import torch
     if devices is None:

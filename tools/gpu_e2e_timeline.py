@@ -20,7 +20,7 @@ def launch(self, ch, stages=7 | 8):
     evs.append((a, b, ch["cnt"]["n_points"], time.perf_counter()))     # with lanes > 1 the groups overlap: the gaps are not idle time
 Engine.launch = launch
 import itertools
-CFG = [(40, 5, 2)]     # (first_group, growth, lanes): the defaults of run_points
+CFG = [(40, 5, 2)]     # (first_group, growth, lanes): the defaults of run_points; add tuples to compare
 for (fg, gr, ln), rep in itertools.product(CFG, range(4)):
     par = slice_params(pts, rep)
     torch.cuda.synchronize()
