@@ -14,7 +14,7 @@
 //   solve_pdi_kernel    warp per system                 back-substitution of the 3-species cascade equation,
 //                                                       fused with the 17 sigma(E)*F(E) rate integrals
 //   matrix_kernel       block (8 warps) per point       exact piecewise T-integral; 9x9 expm, decay matrices, Yf by warp 0
-//   transfer_kernel     thread per matrix               fast-parameter path: expm(f*mpdi+mdcy) and Yf only
+//   transfer_kernel     warp per matrix                 fast-parameter path: expm(f*mpdi+mdcy) and Yf only
 //
 // The sum over grid nodes of the shared-grid kernels is a dense FP64 contraction and runs on the FP64 tensor path
 // (mma.sync m8n8k4 f64 -> DMMA; tcgen05 has no FP64 type); the bound is the FP64 pipe -- which DFMA and DMMA share on
@@ -1030,18 +1030,7 @@ __constant__ const signed char kReacFinal[ACRO_NR][ACRO_NY] = {
     {0, 1, 0, 0, 0, 0, 1, 0, 0},   // 16 Be7+a>p+Li6
     {1, 2, 0, 0, 0, 1, 0, 0, 0}};  // 17 Be7+a>p+p+n+He4
 
-// ---- 9x9 helpers (row-major, thread-local) ----
-__device__ inline void mm9(const double* A, const double* B, double* C) {
-    for (int i = 0; i < 9; ++i)
-        for (int j = 0; j < 9; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < 9; ++k) s = fma(A[i * 9 + k], B[k * 9 + j], s);
-            C[i * 9 + j] = s;
-        }
-}
-
-// the entry-wise combinations of the Pade-13 numerator/denominator, shared by the serial and the warp-cooperative form so that
-// both round alike (explicit fma: no dependence on what the compiler contracts)
+// the entry-wise combinations of the Pade-13 numerator/denominator (explicit fma: no dependence on what the compiler contracts)
 __device__ __forceinline__ double pade_w1(const double* b, double a2, double a4, double a6, int top) {
     return fma(b[top - 4], a2, fma(b[top - 2], a4, b[top] * a6));                      // b_top A6 + b_(top-2) A4 + b_(top-4) A2
 }
@@ -1055,10 +1044,11 @@ __device__ __forceinline__ double pade_v2(const double* b, double v, double a2, 
 __constant__ const double kPade13[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
                                          10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
 
-// ---- the same algorithm by one warp on matrices in shared memory: lane e (+32, +64) owns entry e of every 9x9 product.
-// Every entry is computed with the operations and the order of the serial form below (which transfer_kernel keeps, one thread
-// per job): the two agree bit for bit (tests/test_gpu_models.py::test_matrix_stage_equals_transfer_kernel).  The serial form
-// in matrix_kernel was 130 k dependent instructions of ONE lane per point: 0.2 ms of a single point's 0.67 ms device latency.
+// ---- 9x9 matrix exponential, Pade-13 scaling and squaring (Higham 2005, the algorithm behind scipy.linalg.expm used at
+// models.py:130), by one warp on matrices in shared memory: lane e (+32, +64) owns entry e of every 9x9 product.  Rounds
+// entry for entry like the one-thread form it replaced (rounds 1-2: 255 registers, 5.6 kB of local memory, 130 k dependent
+// instructions of ONE lane per point -- 0.2 ms of a single point's 0.67 ms device latency).  matrix_kernel and transfer_kernel
+// share it: a point's abundances are the same bits on both routes (tests: test_matrix_stage_equals_transfer_kernel).
 __device__ __forceinline__ void mm9w(const double* A, const double* B, double* C, int lane) {
     for (int e = lane; e < 81; e += 32) {
         const int i = e / 9, j = e - 9 * i;
@@ -1143,11 +1133,25 @@ __device__ void expm9_warp(const double* Ain, double* R, double* ws, int lane) {
     }
 }
 
-// apply_transfer (below) by one warp; A and the scratch ws (9 x 81 doubles) in shared memory.  Lane 0 returns the flag.
+// Yf = postd . expm(A) . pred . Y0 for the three abundance columns (models.py:77-89,133-157), by one warp; A and the scratch ws
+// (9 x 81 doubles) in shared memory.  Lane 0 returns the flag.  expm_out (global, optional): the plain exponential of A.
 __device__ void apply_transfer_warp(const double* A, double t_at_tmax, const double* Y0, double* Yf /*global [9][3]*/, int* nonfinite,
-                                    double* ws, int lane) {
+                                    double* ws, int lane, double* expm_out = nullptr) {
     double* B = ws + 7 * 81;
     double* R = ws + 8 * 81;
+    if (expm_out) {            // the plain exponential, for callers that ask for it (models.py:130)
+        expm9_warp(A, R, ws, lane);
+        for (int e = lane; e < 81; e += 32) expm_out[e] = R[e];
+        __syncwarp();
+    }
+    // For the abundances the free-neutron decay is folded out of the matrix first.  Neutrons (row/column 0) are never a
+    // target: their column is pure decay into protons and the proton column is empty; the pre-decay below empties the
+    // neutron entry and the post-decay adds whatever neutrons remain to the protons.  So Y_n + Y_p and every other nuclide
+    // do not depend on the neutron lifetime at all, and  exp(A) -> exp(B)  with  B = A, column n := 0, row p += row n,
+    // row n := 0  gives the SAME transfer -- exactly, for any rate -- while ||B||_1 no longer contains rate x time of the
+    // neutron (1.45e9 at tau = 7.5e8 s, ||B||_1 = 2.3e3).  Scaling and squaring doubles the rounding error of the Pade
+    // solve with every squaring, 29 of them for ||A||_1 = 1.45e9: nucleon number drifted by 7.7e-8 (SciPy: 3e-9 on the same
+    // matrix); with the fold the abundances agree with a 60-digit evaluation to 6e-14 (tools/proto/expm_fold_study.py).
     bool foldable = (A[0 * 9 + 0] + A[1 * 9 + 0] == 0.0);
     for (int i = 2; i < 9; ++i) foldable = foldable && A[i * 9 + 0] == 0.0;
     for (int i = 0; i < 9; ++i) foldable = foldable && A[i * 9 + 1] == 0.0;
@@ -1181,109 +1185,6 @@ __device__ void apply_transfer_warp(const double* A, double t_at_tmax, const dou
         for (int i = 0; i < 9; ++i) { Yf[i * 3 + c] = z[i]; bad |= !isfinite(z[i]); }
     }
     if (__any_sync(0xffffffffu, bad) && lane == 0) *nonfinite = 1;
-}
-
-// Pade-13 scaling and squaring (Higham 2005, the algorithm behind scipy.linalg.expm used at models.py:130)
-__device__ void expm9(const double* Ain, double* R) {
-    const double* b = kPade13;
-    double A[81], A2[81], A4[81], A6[81], U[81], V[81], W[81];
-    double nrm = 0.0;
-    for (int j = 0; j < 9; ++j) {
-        double c = 0.0;
-        for (int i = 0; i < 9; ++i) c += fabs(Ain[i * 9 + j]);
-        nrm = fmax(nrm, c);
-    }
-    int s = 0;
-    if (nrm > 5.371920351148152) s = (int)fmax(0.0, ceil(log2(nrm / 5.371920351148152)));
-    const double sc = ldexp(1.0, -s);
-    for (int i = 0; i < 81; ++i) A[i] = Ain[i] * sc;
-    mm9(A, A, A2); mm9(A2, A2, A4); mm9(A4, A2, A6);
-    for (int i = 0; i < 81; ++i) W[i] = pade_w1(b, A2[i], A4[i], A6[i], 13);
-    mm9(A6, W, V);   // V = A6*W (temp)
-    for (int i = 0; i < 81; ++i) W[i] = pade_w2(b, V[i], A2[i], A4[i], A6[i], 7, i % 10 == 0);
-    mm9(A, W, U);
-    for (int i = 0; i < 81; ++i) W[i] = pade_w1(b, A2[i], A4[i], A6[i], 12);
-    mm9(A6, W, V);
-    for (int i = 0; i < 81; ++i) V[i] = pade_v2(b, V[i], A2[i], A4[i], A6[i], 6, i % 10 == 0);
-    // solve (V-U) R = (V+U) by LU with partial pivoting
-    for (int i = 0; i < 81; ++i) { W[i] = V[i] - U[i]; R[i] = V[i] + U[i]; }
-    for (int c = 0; c < 9; ++c) {
-        int piv = c;
-        double best = fabs(W[c * 9 + c]);
-        for (int r = c + 1; r < 9; ++r) { const double v = fabs(W[r * 9 + c]); if (v > best) { best = v; piv = r; } }
-        if (piv != c)
-            for (int k = 0; k < 9; ++k) {
-                double t = W[c * 9 + k]; W[c * 9 + k] = W[piv * 9 + k]; W[piv * 9 + k] = t;
-                t = R[c * 9 + k]; R[c * 9 + k] = R[piv * 9 + k]; R[piv * 9 + k] = t;
-            }
-        const double ip = 1.0 / W[c * 9 + c];
-        for (int r = c + 1; r < 9; ++r) {
-            const double f = W[r * 9 + c] * ip;
-            if (f == 0.0) continue;
-            for (int k = c; k < 9; ++k) W[r * 9 + k] = fma(-f, W[c * 9 + k], W[r * 9 + k]);
-            for (int k = 0; k < 9; ++k) R[r * 9 + k] = fma(-f, R[c * 9 + k], R[r * 9 + k]);
-        }
-    }
-    for (int c = 8; c >= 0; --c) {
-        const double ip = 1.0 / W[c * 9 + c];
-        for (int k = 0; k < 9; ++k) {
-            double v = R[c * 9 + k];
-            for (int cc = c + 1; cc < 9; ++cc) v = fma(-W[c * 9 + cc], R[cc * 9 + k], v);
-            R[c * 9 + k] = v * ip;
-        }
-    }
-    for (int q = 0; q < s; ++q) {
-        mm9(R, R, W);
-        for (int i = 0; i < 81; ++i) R[i] = W[i];
-    }
-}
-
-// Yf = postd . expm(A) . pred . Y0 for the three abundance columns (models.py:77-89,133-157)
-__device__ void apply_transfer(const double* A, double t_at_tmax, const double* Y0 /*[9][3]*/, double* expm_out,
-                               double* Yf /*[9][3]*/, int* nonfinite) {
-    double R[81];
-    if (expm_out) {            // the plain exponential, for callers that ask for it (models.py:130)
-        expm9(A, R);
-        for (int i = 0; i < 81; ++i) expm_out[i] = R[i];
-    }
-    // For the abundances the free-neutron decay is folded out of the matrix first.  Neutrons (row/column 0) are never a
-    // target: their column is pure decay into protons and the proton column is empty; the pre-decay below empties the
-    // neutron entry and the post-decay adds whatever neutrons remain to the protons.  So Y_n + Y_p and every other nuclide
-    // do not depend on the neutron lifetime at all, and  exp(A) -> exp(B)  with  B = A, column n := 0, row p += row n,
-    // row n := 0  gives the SAME transfer -- exactly, for any rate -- while ||B||_1 no longer contains rate x time of the
-    // neutron (1.45e9 at tau = 7.5e8 s, ||B||_1 = 2.3e3).  Scaling and squaring doubles the rounding error of the Pade
-    // solve with every squaring, 29 of them for ||A||_1 = 1.45e9: nucleon number drifted by 7.7e-8 (SciPy: 3e-9 on the same
-    // matrix); with the fold the abundances agree with a 60-digit evaluation to 6e-14 (tools/proto/expm_fold_study.py).
-    double B[81];
-    bool foldable = (A[0 * 9 + 0] + A[1 * 9 + 0] == 0.0);
-    for (int i = 2; i < 9; ++i) foldable = foldable && A[i * 9 + 0] == 0.0;
-    for (int i = 0; i < 9; ++i) foldable = foldable && A[i * 9 + 1] == 0.0;
-    for (int i = 0; i < 81; ++i) B[i] = A[i];
-    if (foldable) {
-        for (int i = 0; i < 9; ++i) B[i * 9 + 0] = 0.0;
-        for (int k = 0; k < 9; ++k) { B[1 * 9 + k] += B[0 * 9 + k]; B[0 * 9 + k] = 0.0; }
-    }
-    expm9(B, R);
-    const double ef = exp(-t_at_tmax / kTauT);
-    bool bad = false;
-    for (int c = 0; c < 3; ++c) {
-        double y[9], z[9];
-        for (int i = 0; i < 9; ++i) y[i] = Y0[i * 3 + c];
-        // pre-decay: n -> p completely, t -> He3 by exp(-t(Tmax)/tau_t)
-        y[1] += y[0]; y[0] = 0.0;
-        y[4] += (1.0 - ef) * y[3]; y[3] = ef * y[3];
-        for (int i = 0; i < 9; ++i) {
-            double v = 0.0;
-            for (int k = 0; k < 9; ++k) v = fma(R[i * 9 + k], y[k], v);
-            z[i] = v;
-        }
-        // post-decay: n -> p, t -> He3, Be7 -> Li7
-        z[1] += z[0]; z[0] = 0.0;
-        z[4] += z[3]; z[3] = 0.0;
-        z[7] += z[8]; z[8] = 0.0;
-        for (int i = 0; i < 9; ++i) { Yf[i * 3 + c] = z[i]; bad |= !isfinite(z[i]); }
-    }
-    if (bad) *nonfinite = 1;
 }
 
 // int_{x1}^{x2} 10^{alpha x + beta} ln10 dx, stable for any alpha (evaluated from the larger end)
@@ -1424,21 +1325,24 @@ __global__ void __launch_bounds__(256) matrix_kernel(int n_points, const int32_t
     if (status_out) status_out[pt] = st;
 }
 
-__global__ void __launch_bounds__(64) transfer_kernel(int n, const double* __restrict__ mpdi, const double* __restrict__ mdcy,
-                                                      const int32_t* __restrict__ matrix_index,
-                                                      const double* __restrict__ factor, const double* __restrict__ t_at_tmax,
-                                                      double* __restrict__ expm_out, double* __restrict__ Yf_out,
-                                                      int32_t* __restrict__ status, DeviceTables t) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Fast-parameter path: one warp per job (a rescaling of a buffered matrix pair), four jobs per block.
+__global__ void __launch_bounds__(128) transfer_kernel(int n, const double* __restrict__ mpdi, const double* __restrict__ mdcy,
+                                                       const int32_t* __restrict__ matrix_index,
+                                                       const double* __restrict__ factor, const double* __restrict__ t_at_tmax,
+                                                       double* __restrict__ expm_out, double* __restrict__ Yf_out,
+                                                       int32_t* __restrict__ status, DeviceTables t) {
+    __shared__ double s_mx[4][10 * 81];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 4 + warp;
     if (i >= n) return;
-    double A[81], Yf[27];
+    double* A = s_mx[warp];
     const double f = factor ? factor[i] : 1.0;
     const int64_t m = matrix_index ? matrix_index[i] : i;       // many rescalings of one (mpdi, mdcy) pair share its storage
-    for (int k = 0; k < 81; ++k) A[k] = f * mpdi[m * 81 + k] + mdcy[m * 81 + k];
+    for (int k = lane; k < 81; k += 32) A[k] = f * mpdi[m * 81 + k] + mdcy[m * 81 + k];
+    __syncwarp();
     int bad = 0;
-    apply_transfer(A, t_at_tmax[i], t.Y0, expm_out ? expm_out + (int64_t)i * 81 : nullptr, Yf, &bad);
-    for (int k = 0; k < 27; ++k) Yf_out[(int64_t)i * 27 + k] = Yf[k];
-    if (status) status[i] = bad ? ACRO_ST_NONFINITE : 0;
+    apply_transfer_warp(A, t_at_tmax[i], t.Y0, Yf_out + (int64_t)i * 27, &bad, A + 81, lane, expm_out ? expm_out + (int64_t)i * 81 : nullptr);
+    if (lane == 0 && status) status[i] = bad ? ACRO_ST_NONFINITE : 0;
 }
 
 // total rates for arbitrary (E,T) pairs -> out[n][3]
@@ -1630,7 +1534,7 @@ cudaError_t launch_transfer(int n, const double* mpdi, const double* mdcy, const
                             double* expm_out, double* Yf, int32_t* status, const DeviceTables& t, cudaStream_t st,
                             LaunchCounters& lc) {
     if (n == 0) return cudaSuccess;
-    transfer_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, mpdi, mdcy, matrix_index, factor, t_at_tmax, expm_out, Yf, status, t);
+    transfer_kernel<<<(n + 3) / 4, 128, 0, st>>>(n, mpdi, mdcy, matrix_index, factor, t_at_tmax, expm_out, Yf, status, t);
     lc.launches++;
     return cudaGetLastError();
 }

@@ -438,8 +438,8 @@ def test_closed_form_photon_plane_corners(gpu_engine, xcheck_engine):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", POINTS)
 def test_matrix_stage_equals_transfer_kernel(gpu_engine, results, name):
-    """matrix_kernel exponentiates by one warp on shared-memory matrices (expm9_warp), transfer_kernel by one thread per job
-    (expm9): the same operations in the same order per matrix entry, so the abundances agree bit for bit."""
+    """matrix_kernel (warp 0 of a point's block) and transfer_kernel (one warp per job) share the warp-cooperative exponential
+    and transfer: a point's abundances are the same bits on the scan route and on the fast-parameter route."""
     z, sp, r = results[name]
     Y = gpu_engine.transfer(r["mpdi"].reshape(1, 9, 9), r["mdcy"].reshape(1, 9, 9), 1.0, sp.t_at_tmax)
     assert np.array_equal(Y[0], r["Yf"].reshape(-1, 9, 3)[0])
