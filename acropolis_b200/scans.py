@@ -222,6 +222,7 @@ def run_points(model, param_sets, devices=None, group=4096, first_group=40, grow
         models = [model(**p) for p in param_sets]
         Yf = run_models(models, devices=devices)
         return np.array([[*[p[k] for k in sorted(p)], *Y.transpose().reshape(Y.size)] for p, Y in zip(param_sets, Yf)])
+    lanes = int(os.environ.get("ACROPOLIS_B200_LANES", lanes))      # 1 = every group on one stream, one after the other
     rows, eng, in_flight = [None] * N, None, []
     # The loop below allocates thousands of small objects per call; a generation-2 collection in the middle of it walks
     # every cached grid and model (tens of ms, seen as 30-50 ms holes in tools/gpu_e2e_timeline.py) while the GPU runs dry.
