@@ -81,9 +81,51 @@ def estimate_tempkd_ee(mchi, delta, gammad, gammav, nd, S, ii, sigma_ee):
         Ncol = max(1., mchi / T)
         return log(_sigma_v_ee(T) * _nee(T) / ii.hubble_rate(T) / Ncol)
 
+    def _root_grid(logT):
+        """_root for an array of log T: the same expressions with T as a column and the Bessel-function regimes of _kernel as
+        masks.  Only used to LOCATE the sign changes (400 scalar calls with a 128-node integral each were 23 of the 25 ms of a
+        ResonanceModel constructor); the root itself is refined with the scalar function below."""
+        T = np.clip(np.exp(logT), Tmin, Tmax)
+        out = np.empty(len(T))
+        xe_all, xchi_all = me / T, mchi / T
+        regimes = (xe_all < 400) & (400 < xchi_all), xe_all > 400
+        regimes = regimes + (~(regimes[0] | regimes[1]),)
+        for which, mask in enumerate(regimes):
+            if not np.any(mask):
+                continue
+            Tc = T[mask][:, None]
+
+            def kern(lz):
+                z = np.exp(lz)
+                s = (z + me + mchi)**2.
+                sqrt_s = np.sqrt(s)
+                sigma = sigma_ee(s=s, mchi=mchi, delta=delta, gammad=gammad, gammav=gammav)
+                ye, ychi, ys = Tc / me, Tc / mchi, Tc / sqrt_s
+                if which == 0:
+                    bessel = np.exp(-(z + me) / Tc) * _k1(ys) / _k2(ychi) / kn(2, me / Tc)
+                elif which == 1:
+                    bessel = np.exp(-z / Tc) * _k1(ys) / (_k2(ychi) * _k2(ye))
+                else:
+                    bessel = kn(1, sqrt_s / Tc) / (kn(2, me / Tc) * kn(2, mchi / Tc))
+                return z * (2. * sqrt_s) * sigma * (s - (me + mchi)**2.) * (s - (me - mchi)**2.) * bessel / sqrt_s
+
+            Tm = T[mask]
+            sv = _gl(kern, np.log(Tm / fac), np.log(fac * Tm), 128) / (8. * me**2. * mchi**2. * Tm)
+            xe = (me / Tm)[:, None]
+            tmax = np.sqrt(np.maximum(fac - me / Tm, 0.))
+            with np.errstate(over="ignore"):      # rows with me/T >= fac are discarded by the where() below
+                f = _gl(lambda t: (xe + t * t) * np.sqrt(np.maximum((xe + t * t)**2. - xe**2., 0.)) / (np.exp(xe + t * t) + 1.) * 2. * t,
+                        np.zeros_like(tmax), tmax, 128)
+            nee_1 = 4. * np.where(me / Tm < fac, f, 0.) * (Tm**3.) / (2. * pi2)
+            Y = ii.bbn_abundances_0()
+            nee_2 = (Y[1] + 2. * Y[5]) * ii.parameter('eta') * (2. * zeta3 / pi2) * (Tm**3.)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                out[mask] = np.log(sv * np.maximum(nee_1, nee_2) / ii.hubble_rate(Tm) / np.maximum(1., mchi / Tm))
+        return out
+
     x0 = log(mchi)
     grid = np.linspace(log(Tmin), log(Tmax), 400)
-    vals = np.array([_root(g) for g in grid])
+    vals = _root_grid(grid)
     sc = np.where(np.sign(vals[:-1]) * np.sign(vals[1:]) < 0)[0]
     tempkd = np.nan
     if len(sc):
